@@ -1,0 +1,93 @@
+/* litho_b200.h -- C ABI of the B200-native Abbe imaging hot path.
+ *
+ * Drop-in boundary for the partially coherent aerial-image path of
+ * quarterwave0/LithographySimulator.  The reference has no FFI layer of its own: its
+ * boundary is the Python call surface.  Every entry point below
+ * names the reference interface it replaces (file:line relative to the reference root);
+ * lithographysimulator_b200/imageformation.py binds them with ctypes and mirrors the
+ * reference signatures (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *   - all data pointers are DEVICE pointers on the current CUDA device unless named *_host;
+ *   - planes are row-major; complex64 is interleaved (re, im) float pairs;
+ *   - calls are asynchronous on `stream` (a cudaStream_t passed as void*) unless stated;
+ *   - the caller owns every buffer including the workspace; a plan owns only its twiddle table;
+ *   - return 0 on success, non-zero on error with a message in litho_last_error();
+ *   - re-entrant per plan/stream pair.
+ */
+#ifndef LITHO_B200_H
+#define LITHO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LITHO_OK 0
+#define LITHO_ERR_ARG 1      /* invalid argument / unsupported configuration */
+#define LITHO_ERR_CUDA 2     /* CUDA runtime error */
+#define LITHO_ERR_WORKSPACE 3
+
+#define LITHO_ABI_VERSION 1
+
+typedef struct litho_plan litho_plan_t;
+
+typedef struct litho_plan_info {
+    int pn, N;            /* grid side, FFT-approximation length (mask.py:67-72) */
+    int bbox[4];          /* pupil support r0,r1,c0,c1 (inclusive) */
+    int L, M, R, Wr;      /* transform length, sub-FFT length, residues, per-residue pitch */
+    int path;             /* 1 = fine grid (exact for any source) */
+    int default_batch;    /* source points per launch pair used when batch <= 0 */
+    uint64_t intensity_elems; /* float elements of the residue-major intensity plane */
+} litho_plan_info_t;
+
+int litho_abi_version(void);
+const char* litho_last_error(void);
+/* 1 if this library was built for the GPU (sm_100a), 0 for the CPU emulation used by tests */
+int litho_is_device_build(void);
+
+/* Mask.calculateEpsilonN / _nearest2SqInt                           mask.py:63-72
+ * host-only helper: beta = wavelength/(deltaK*pixelSize), N = nearest power of two, eps = N/beta */
+int litho_epsilon_n(double deltaK, double pixelSize, double wavelength, double* eps, int* N);
+
+/* Bounding box of the non-zero pupil samples (the support that roll(), imageformation.py:63,
+ * moves around the grid).  Synchronises `stream`; bbox_host = {r0,r1,c0,c1}, {0,-1,0,-1} if empty. */
+int litho_pupil_bbox(const void* pupil, int pn, int* bbox_host, void* stream);
+
+/* Plan for abbeImage(fft=True) on a pn x pn grid with FFT-approximation length N.
+ * flags: reserved, pass 0. */
+int litho_plan_create(int pn, int N, const int* bbox, int flags, litho_plan_t** plan);
+void litho_plan_destroy(litho_plan_t* plan);
+int litho_plan_get_info(const litho_plan_t* plan, litho_plan_info_t* info);
+size_t litho_plan_workspace_bytes(const litho_plan_t* plan, int batch);
+
+/* The hot loop of abbeImage                                  imageformation.py:59-67
+ *   intensity += sum_s w_s * | centred zoom IDFT_N { roll(pupil, shift_s) * maskFT } |^2
+ * shifts: n_src (d0,d1) int32 pairs = argwhere(lightsource) - pn//2 (imageformation.py:59);
+ * weights: n_src floats or NULL (the reference ignores source values: all ones);
+ * intensity: plan.intensity_elems floats in the plan's residue-major order, accumulated into
+ *            (zero it before the first call; partial planes from several GPUs may simply be summed). */
+int litho_abbe_fft_accumulate(const litho_plan_t* plan, const void* maskFT, const void* pupil,
+                              const int32_t* shifts, const float* weights, int n_src, int batch,
+                              float* intensity, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Post-processing of abbeImage(fft=True)                      imageformation.py:69-75
+ * abs -> bilinear resample by 1/eps -> zero border; out has litho_fft_output_side(pn,eps)^2 floats. */
+int litho_fft_output_side(int pn, double eps);
+int litho_abbe_fft_finalize(const litho_plan_t* plan, const float* intensity, double eps, float* out,
+                            void* stream);
+/* Raw accumulated intensity in natural row-major order (pn x pn), no resampling. */
+int litho_abbe_fft_unpermute(const litho_plan_t* plan, const float* intensity, float* out, void* stream);
+
+/* calculateFFTAerial(pf, maskFFFT, pixelNumber, N)              imageformation.py:32-45
+ * complex field (pn x pn complex64) of one already-shifted pupil `pf`; the plan must have been
+ * created from the bounding box of `pf`. */
+int litho_fft_field(const litho_plan_t* plan, const void* pf, const void* maskFT, void* field,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LITHO_B200_H */

@@ -1,0 +1,150 @@
+"""ctypes binding of the C ABI in include/litho_b200.h.
+
+The product path loads ``liblitho_b200.so`` (sm_100a device code, built in-tree by
+``__graft_entry__.build()`` / ``csrc/Makefile``) and fails loudly when it is missing:
+there is no CPU fallback.  ``NativeLib(path)`` with an explicit path exists so that the
+tests can point the very same binding at the CPU emulation of the kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+DEVICE_LIB = os.path.join(_HERE, "liblitho_b200.so")
+
+
+class LithoError(RuntimeError):
+    pass
+
+
+class PlanInfo(C.Structure):
+    _fields_ = [("pn", C.c_int), ("N", C.c_int), ("bbox", C.c_int * 4), ("L", C.c_int), ("M", C.c_int),
+                ("R", C.c_int), ("Wr", C.c_int), ("path", C.c_int), ("default_batch", C.c_int),
+                ("intensity_elems", C.c_uint64)]
+
+
+# every symbol include/litho_b200.h declares: (name, restype, argtypes)
+_P = C.c_void_p
+SYMBOLS = [
+    ("litho_abi_version", C.c_int, []),
+    ("litho_last_error", C.c_char_p, []),
+    ("litho_is_device_build", C.c_int, []),
+    ("litho_epsilon_n", C.c_int, [C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    ("litho_pupil_bbox", C.c_int, [_P, C.c_int, C.POINTER(C.c_int), _P]),
+    ("litho_plan_create", C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(_P)]),
+    ("litho_plan_destroy", None, [_P]),
+    ("litho_plan_get_info", C.c_int, [_P, C.POINTER(PlanInfo)]),
+    ("litho_plan_workspace_bytes", C.c_size_t, [_P, C.c_int]),
+    ("litho_abbe_fft_accumulate", C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P, C.c_size_t, _P]),
+    ("litho_fft_output_side", C.c_int, [C.c_int, C.c_double]),
+    ("litho_abbe_fft_finalize", C.c_int, [_P, _P, C.c_double, _P, _P]),
+    ("litho_abbe_fft_unpermute", C.c_int, [_P, _P, _P, _P]),
+    ("litho_fft_field", C.c_int, [_P, _P, _P, _P, _P, C.c_size_t, _P]),
+]
+
+
+class NativeLib:
+    """Loaded shared library with typed entry points."""
+
+    def __init__(self, path: str):
+        if not os.path.exists(path):
+            raise LithoError(
+                f"native library not found: {path}. Build it with `python -c 'import __graft_entry__ as g; "
+                f"g.build()'` or `make -C lithographysimulator_b200/csrc`. There is no CPU fallback.")
+        self.path = path
+        self.lib = C.CDLL(path)
+        for name, restype, argtypes in SYMBOLS:
+            fn = getattr(self.lib, name)  # AttributeError if the library does not export it
+            fn.restype = restype
+            fn.argtypes = argtypes
+            setattr(self, name, fn)
+        if self.litho_abi_version() != 1:
+            raise LithoError("ABI version mismatch")
+
+    def check(self, rc: int, what: str = ""):
+        if rc != 0:
+            msg = self.litho_last_error()
+            raise LithoError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")
+
+    # ---- thin typed helpers (pointers are plain ints) --------------------------------------
+    def epsilon_n(self, deltaK: float, pixelSize: float, wavelength: float):
+        eps = C.c_double()
+        n = C.c_int()
+        self.check(self.litho_epsilon_n(deltaK, pixelSize, wavelength, C.byref(eps), C.byref(n)), "litho_epsilon_n")
+        return eps.value, n.value
+
+    def pupil_bbox(self, pupil_ptr: int, pn: int, stream: int = 0):
+        box = (C.c_int * 4)()
+        self.check(self.litho_pupil_bbox(pupil_ptr, pn, box, stream), "litho_pupil_bbox")
+        return tuple(box)
+
+    def plan_create(self, pn: int, N: int, bbox, flags: int = 0) -> "Plan":
+        box = (C.c_int * 4)(*bbox)
+        handle = _P()
+        self.check(self.litho_plan_create(pn, N, box, flags, C.byref(handle)), "litho_plan_create")
+        return Plan(self, handle)
+
+
+class Plan:
+    def __init__(self, lib: NativeLib, handle):
+        self.lib = lib
+        self.handle = handle
+        info = PlanInfo()
+        lib.check(lib.litho_plan_get_info(handle, C.byref(info)), "litho_plan_get_info")
+        self.info = info
+        self.pn, self.N, self.M, self.R, self.Wr = info.pn, info.N, info.M, info.R, info.Wr
+        self.bbox = tuple(info.bbox)
+        self.intensity_elems = int(info.intensity_elems)
+        self.default_batch = info.default_batch
+
+    def workspace_bytes(self, batch: int = 0) -> int:
+        return int(self.lib.litho_plan_workspace_bytes(self.handle, batch))
+
+    def accumulate(self, maskFT, pupil, shifts, weights, n_src, batch, intensity, workspace, workspace_bytes, stream=0):
+        self.lib.check(self.lib.litho_abbe_fft_accumulate(self.handle, maskFT, pupil, shifts, weights, n_src, batch,
+                                                          intensity, workspace, workspace_bytes, stream),
+                       "litho_abbe_fft_accumulate")
+
+    def output_side(self, eps: float) -> int:
+        return int(self.lib.litho_fft_output_side(self.pn, eps))
+
+    def finalize(self, intensity, eps, out, stream=0):
+        self.lib.check(self.lib.litho_abbe_fft_finalize(self.handle, intensity, eps, out, stream),
+                       "litho_abbe_fft_finalize")
+
+    def unpermute(self, intensity, out, stream=0):
+        self.lib.check(self.lib.litho_abbe_fft_unpermute(self.handle, intensity, out, stream),
+                       "litho_abbe_fft_unpermute")
+
+    def fft_field(self, pf, maskFT, field, workspace, workspace_bytes, stream=0):
+        self.lib.check(self.lib.litho_fft_field(self.handle, pf, maskFT, field, workspace, workspace_bytes, stream),
+                       "litho_fft_field")
+
+    def close(self):
+        if self.handle:
+            self.lib.litho_plan_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_lock = threading.Lock()
+_device_lib: NativeLib | None = None
+
+
+def device_lib() -> NativeLib:
+    """The sm_100a library.  Raises LithoError if it has not been built (no fallback)."""
+    global _device_lib
+    with _lock:
+        if _device_lib is None:
+            lib = NativeLib(DEVICE_LIB)
+            if not lib.litho_is_device_build():
+                raise LithoError(f"{DEVICE_LIB} is not a device build")
+            _device_lib = lib
+        return _device_lib

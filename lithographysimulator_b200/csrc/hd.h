@@ -1,0 +1,80 @@
+// Host/device-portable primitives for the Abbe imaging kernels.
+//
+// Every kernel body in this directory is written against a small "thread context"
+// (tid / block ids / sync) so that the very same source compiles (a) as sm_100a device
+// code and (b) as plain C++ that tests/emu runs thread-for-thread on the CPU to check
+// index arithmetic without a GPU.  The CPU build is test infrastructure only; the
+// product library contains the device build alone.
+#pragma once
+#include <math.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define LITHO_HD __host__ __device__ __forceinline__
+#define LITHO_D __device__ __forceinline__
+#else
+#define LITHO_HD inline
+#define LITHO_D inline
+#endif
+
+namespace litho {
+
+struct alignas(8) cplx {
+    float x, y;
+};
+
+LITHO_HD cplx mk(float x, float y) { cplx c; c.x = x; c.y = y; return c; }
+LITHO_HD cplx cadd(cplx a, cplx b) { return mk(a.x + b.x, a.y + b.y); }
+LITHO_HD cplx csub(cplx a, cplx b) { return mk(a.x - b.x, a.y - b.y); }
+LITHO_HD cplx cmul(cplx a, cplx b) { return mk(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+LITHO_HD cplx cconj(cplx a) { return mk(a.x, -a.y); }
+LITHO_HD float cnorm2(cplx a) { return a.x * a.x + a.y * a.y; }
+// multiply by +i / -i
+LITHO_HD cplx mul_pi(cplx a) { return mk(-a.y, a.x); }
+LITHO_HD cplx mul_mi(cplx a) { return mk(a.y, -a.x); }
+
+struct int2_ {
+    int x, y;
+};
+
+// read-only global load (LDG through the non-coherent path on the device)
+LITHO_HD cplx ldg_c(const cplx* p) {
+#if defined(__CUDA_ARCH__)
+    float2 v = __ldg(reinterpret_cast<const float2*>(p));
+    return mk(v.x, v.y);
+#else
+    return *p;
+#endif
+}
+LITHO_HD float ldg_f(const float* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
+// floor-mod for a possibly negative a, b > 0
+LITHO_HD int imod(int a, int b) {
+    int m = a % b;
+    return m < 0 ? m + b : m;
+}
+// ceil(a / b) for b > 0 and any sign of a
+LITHO_HD int cdiv(int a, int b) { return a >= 0 ? (a + b - 1) / b : -((-a) / b); }
+// floor(a / b) for b > 0 and any sign of a
+LITHO_HD int fdiv(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
+
+#if defined(__CUDACC__)
+// Device thread context: thin wrapper over the CUDA built-ins.
+struct DevCtx {
+    __device__ __forceinline__ int tid() const { return threadIdx.x; }
+    __device__ __forceinline__ int bdim() const { return blockDim.x; }
+    __device__ __forceinline__ int bx() const { return blockIdx.x; }
+    __device__ __forceinline__ int by() const { return blockIdx.y; }
+    __device__ __forceinline__ int bz() const { return blockIdx.z; }
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+};
+#endif
+
+}  // namespace litho

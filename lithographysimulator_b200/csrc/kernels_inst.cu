@@ -1,0 +1,104 @@
+// Instantiation unit: compiled once per sub-FFT length with -DLITHO_INST_M=<M>.
+#include "launch.h"
+
+#ifndef LITHO_INST_M
+#error "compile with -DLITHO_INST_M=<sub-FFT length>"
+#endif
+
+#if defined(LITHO_EMU)
+#include "emu_runtime.h"
+#endif
+
+namespace litho {
+
+#if !defined(LITHO_EMU)
+template <int M, int KIND>
+__global__ void __launch_bounds__(RowsShape<M>::THREADS) abbe_rows_kernel(const __grid_constant__ RowsParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    rows_body<M, KIND>(P, DevCtx{}, reinterpret_cast<cplx*>(smem_raw));
+}
+
+template <int M, int EPI>
+__global__ void __launch_bounds__(ColsShape<M>::THREADS) abbe_cols_kernel(const __grid_constant__ ColsParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cols_body<M, EPI>(P, DevCtx{}, reinterpret_cast<cplx*>(smem_raw));
+}
+
+template <class K>
+static int set_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return (int)e;
+    }
+    return 0;
+}
+#endif
+
+template <int M>
+int launch_rows_m(int kind, const RowsParams& P, int gx, int gy, litho_stream_t st) {
+    const size_t smem = (size_t)RowsShape<M>::FPC * FftShape<M>::SMEM_ELEMS * sizeof(cplx);
+    const int threads = RowsShape<M>::THREADS;
+#if defined(LITHO_EMU)
+    (void)st;
+    auto run = [&](auto body) { litho_emu::launch(gx, gy, 1, threads, smem, body); };
+    if (kind == ROW_PUPIL_MASK)
+        run([&](const litho_emu::EmuCtx& c, char* s) { rows_body<M, ROW_PUPIL_MASK>(P, c, (cplx*)s); });
+    else if (kind == ROW_REAL_PLANE)
+        run([&](const litho_emu::EmuCtx& c, char* s) { rows_body<M, ROW_REAL_PLANE>(P, c, (cplx*)s); });
+    else
+        run([&](const litho_emu::EmuCtx& c, char* s) { rows_body<M, ROW_CPLX_PLANE>(P, c, (cplx*)s); });
+    return 0;
+#else
+    dim3 grid(gx, gy, 1), block(threads, 1, 1);
+    int e = 0;
+    if (kind == ROW_PUPIL_MASK) {
+        if ((e = set_smem(abbe_rows_kernel<M, ROW_PUPIL_MASK>, smem))) return e;
+        abbe_rows_kernel<M, ROW_PUPIL_MASK><<<grid, block, smem, st>>>(P);
+    } else if (kind == ROW_REAL_PLANE) {
+        if ((e = set_smem(abbe_rows_kernel<M, ROW_REAL_PLANE>, smem))) return e;
+        abbe_rows_kernel<M, ROW_REAL_PLANE><<<grid, block, smem, st>>>(P);
+    } else {
+        if ((e = set_smem(abbe_rows_kernel<M, ROW_CPLX_PLANE>, smem))) return e;
+        abbe_rows_kernel<M, ROW_CPLX_PLANE><<<grid, block, smem, st>>>(P);
+    }
+    return (int)cudaGetLastError();
+#endif
+}
+
+template <int M>
+int launch_cols_m(int epi, const ColsParams& P, int gx, int gy, litho_stream_t st) {
+    const size_t smem = (size_t)ColsShape<M>::CB * FftShape<M>::SMEM_ELEMS * sizeof(cplx);
+    const int threads = ColsShape<M>::THREADS;
+#if defined(LITHO_EMU)
+    (void)st;
+    auto run = [&](auto body) { litho_emu::launch(gx, gy, 1, threads, smem, body); };
+    if (epi == EPI_ACCUM)
+        run([&](const litho_emu::EmuCtx& c, char* s) { cols_body<M, EPI_ACCUM>(P, c, (cplx*)s); });
+    else
+        run([&](const litho_emu::EmuCtx& c, char* s) { cols_body<M, EPI_FIELD>(P, c, (cplx*)s); });
+    return 0;
+#else
+    dim3 grid(gx, gy, 1), block(threads, 1, 1);
+    int e = 0;
+    if (epi == EPI_ACCUM) {
+        if ((e = set_smem(abbe_cols_kernel<M, EPI_ACCUM>, smem))) return e;
+        abbe_cols_kernel<M, EPI_ACCUM><<<grid, block, smem, st>>>(P);
+    } else {
+        if ((e = set_smem(abbe_cols_kernel<M, EPI_FIELD>, smem))) return e;
+        abbe_cols_kernel<M, EPI_FIELD><<<grid, block, smem, st>>>(P);
+    }
+    return (int)cudaGetLastError();
+#endif
+}
+
+template <int M>
+void shape_m(int* rows_fpc, int* cols_cb) {
+    *rows_fpc = RowsShape<M>::FPC;
+    *cols_cb = ColsShape<M>::CB;
+}
+
+template int launch_rows_m<LITHO_INST_M>(int, const RowsParams&, int, int, litho_stream_t);
+template int launch_cols_m<LITHO_INST_M>(int, const ColsParams&, int, int, litho_stream_t);
+template void shape_m<LITHO_INST_M>(int*, int*);
+
+}  // namespace litho

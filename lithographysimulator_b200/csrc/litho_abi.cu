@@ -1,0 +1,440 @@
+// C ABI of the Abbe imaging hot path (see include/litho_b200.h for the contract).
+// Device build: nvcc -gencode arch=compute_100a,code=sm_100a.  With -DLITHO_EMU the same
+// host logic drives the CPU emulation of the kernels (tests only).
+#include "../../include/litho_b200.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "launch.h"
+
+#if defined(LITHO_EMU)
+#include "emu_runtime.h"
+#endif
+
+using namespace litho;
+
+// --------------------------------------------------------------------------- error state
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+// --------------------------------------------------------------------------- backend
+#if defined(LITHO_EMU)
+static int be_malloc(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 1; }
+static void be_free(void* p) { free(p); }
+static int be_h2d(void* d, const void* h, size_t n, litho_stream_t) { memcpy(d, h, n); return 0; }
+static int be_d2h_sync(void* h, const void* d, size_t n, litho_stream_t) { memcpy(h, d, n); return 0; }
+static const char* be_errstr(int) { return "emu"; }
+#else
+static int be_malloc(void** p, size_t n) { return (int)cudaMalloc(p, n ? n : 1); }
+static void be_free(void* p) { cudaFree(p); }
+static int be_h2d(void* d, const void* h, size_t n, litho_stream_t st) {
+    return (int)cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, st);
+}
+static int be_d2h_sync(void* h, const void* d, size_t n, litho_stream_t st) {
+    cudaError_t e = cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaStreamSynchronize(st);
+}
+static const char* be_errstr(int e) { return cudaGetErrorString((cudaError_t)e); }
+#endif
+
+#define BE_CHECK(expr)                                                                          \
+    do {                                                                                        \
+        int _e = (expr);                                                                        \
+        if (_e != 0) return fail(LITHO_ERR_CUDA, std::string(#expr) + ": " + be_errstr(_e));    \
+    } while (0)
+
+// --------------------------------------------------------------------------- small kernels
+namespace litho {
+
+struct BBoxParams {
+    const cplx* pupil;
+    int pn;
+    int* box;  // {rmin, rmax, cmin, cmax}
+};
+
+LITHO_HD void atomic_min_i(int* p, int v) {
+#if defined(__CUDA_ARCH__)
+    atomicMin(p, v);
+#else
+    if (v < *p) *p = v;
+#endif
+}
+LITHO_HD void atomic_max_i(int* p, int v) {
+#if defined(__CUDA_ARCH__)
+    atomicMax(p, v);
+#else
+    if (v > *p) *p = v;
+#endif
+}
+
+// one CTA per row; threads stride over the columns
+template <class Ctx>
+LITHO_HD void bbox_body(const BBoxParams& P, const Ctx& ctx) {
+    const int row = ctx.bx();
+    int cmin = P.pn, cmax = -1;
+    for (int c = ctx.tid(); c < P.pn; c += ctx.bdim()) {
+        cplx v = P.pupil[(size_t)row * P.pn + c];
+        if (v.x != 0.f || v.y != 0.f) {
+            if (c < cmin) cmin = c;
+            if (c > cmax) cmax = c;
+        }
+    }
+    if (cmax >= 0) {
+        atomic_min_i(P.box + 0, row);
+        atomic_max_i(P.box + 1, row);
+        atomic_min_i(P.box + 2, cmin);
+        atomic_max_i(P.box + 3, cmax);
+    }
+}
+
+struct UnpermParams {
+    PermView in;
+    int pn;
+    float* out;
+};
+
+#if !defined(LITHO_EMU)
+__global__ void bbox_kernel(const __grid_constant__ BBoxParams P) { bbox_body(P, DevCtx{}); }
+__global__ void finalize_kernel(const __grid_constant__ FinalizeParams P) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x < P.out_side) finalize_pixel(P, y, x);
+}
+__global__ void unpermute_kernel(const __grid_constant__ UnpermParams P) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x < P.pn) P.out[(size_t)y * P.pn + x] = P.in.at(y, x);
+}
+#endif
+
+}  // namespace litho
+
+// --------------------------------------------------------------------------- plan
+struct litho_plan {
+    int pn, N;
+    int bbox[4];
+    int Sr, Sc;
+    ZoomPlan zp;
+    AxisOut out;
+    cplx* twL;  // device: w_L[i] = exp(+2*pi*i*i/L)
+    int rows_fpc, cols_cb;
+    int default_batch;
+};
+
+static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+static int dispatch_shape(int M, int* fpc, int* cb) {
+    switch (M) {
+#define X(m) case m: shape_m<m>(fpc, cb); return 0;
+        LITHO_FOR_EACH_M(X)
+#undef X
+    }
+    return 1;
+}
+static int dispatch_rows(int M, int kind, const RowsParams& P, int gx, int gy, litho_stream_t st) {
+    switch (M) {
+#define X(m) case m: return launch_rows_m<m>(kind, P, gx, gy, st);
+        LITHO_FOR_EACH_M(X)
+#undef X
+    }
+    return -1;
+}
+static int dispatch_cols(int M, int epi, const ColsParams& P, int gx, int gy, litho_stream_t st) {
+    switch (M) {
+#define X(m) case m: return launch_cols_m<m>(epi, P, gx, gy, st);
+        LITHO_FOR_EACH_M(X)
+#undef X
+    }
+    return -1;
+}
+
+extern "C" {
+
+int litho_abi_version(void) { return LITHO_ABI_VERSION; }
+const char* litho_last_error(void) { return g_err.c_str(); }
+int litho_is_device_build(void) {
+#if defined(LITHO_EMU)
+    return 0;
+#else
+    return 1;
+#endif
+}
+
+int litho_epsilon_n(double deltaK, double pixelSize, double wavelength, double* eps, int* N) {
+    if (!(deltaK > 0) || !(pixelSize > 0) || !(wavelength > 0)) return fail(LITHO_ERR_ARG, "epsilon_n: non-positive argument");
+    const double beta = 1.0 / ((deltaK * pixelSize) / wavelength);
+    // mask.py:63-65: argmin over {2,4,...,16384} of |2^k - beta| evaluated in float32, first wins
+    int best = 2;
+    float bestd = fabsf(2.0f - (float)beta);
+    for (int k = 2; k <= 14; ++k) {
+        const float d = fabsf((float)(1 << k) - (float)beta);
+        if (d < bestd) {
+            bestd = d;
+            best = 1 << k;
+        }
+    }
+    if (N) *N = best;
+    if (eps) *eps = (double)best / beta;
+    return LITHO_OK;
+}
+
+int litho_pupil_bbox(const void* pupil, int pn, int* bbox_host, void* stream) {
+    if (!pupil || pn <= 0 || !bbox_host) return fail(LITHO_ERR_ARG, "pupil_bbox: bad argument");
+    litho_stream_t st = (litho_stream_t)stream;
+    int* dbox = nullptr;
+    BE_CHECK(be_malloc((void**)&dbox, 4 * sizeof(int)));
+    int init[4] = {pn, -1, pn, -1};
+    int rc = be_h2d(dbox, init, sizeof(init), st);
+    if (rc == 0) {
+        BBoxParams P{(const cplx*)pupil, pn, dbox};
+#if defined(LITHO_EMU)
+        litho_emu::launch(pn, 1, 1, 32, 0, [&](const litho_emu::EmuCtx& c, char*) { bbox_body(P, c); });
+#else
+        bbox_kernel<<<pn, 256, 0, st>>>(P);
+        rc = (int)cudaGetLastError();
+#endif
+    }
+    if (rc == 0) rc = be_d2h_sync(bbox_host, dbox, 4 * sizeof(int), st);
+    be_free(dbox);
+    if (rc != 0) return fail(LITHO_ERR_CUDA, std::string("pupil_bbox: ") + be_errstr(rc));
+    if (bbox_host[1] < 0) {
+        bbox_host[0] = 0; bbox_host[1] = -1; bbox_host[2] = 0; bbox_host[3] = -1;
+    }
+    return LITHO_OK;
+}
+
+int litho_plan_create(int pn, int N, const int* bbox, int flags, litho_plan_t** out) {
+    (void)flags;
+    if (!out || !bbox) return fail(LITHO_ERR_ARG, "plan_create: null argument");
+    if (pn < 2 || (pn & 1)) return fail(LITHO_ERR_ARG, "plan_create: pixelNumber must be even and >= 2 (odd grids make the reference transform length N-1)");
+    if (!is_pow2(N) || N > 16384 || N < 16) return fail(LITHO_ERR_ARG, "plan_create: N must be a power of two in [16,16384]");
+    if (N < pn) return fail(LITHO_ERR_ARG, "plan_create: N < pixelNumber is unsupported (the reference raises, SURVEY Q7)");
+    int r0 = bbox[0], r1 = bbox[1], c0 = bbox[2], c1 = bbox[3];
+    if (r1 < r0 || c1 < c0) {  // empty pupil: keep a 1x1 window so the kernels have something to do
+        r0 = r1 = c0 = c1 = pn / 2;
+    }
+    if (r0 < 0 || c0 < 0 || r1 >= pn || c1 >= pn) return fail(LITHO_ERR_ARG, "plan_create: bbox outside the grid");
+    litho_plan* p = new litho_plan();
+    p->pn = pn; p->N = N;
+    p->bbox[0] = r0; p->bbox[1] = r1; p->bbox[2] = c0; p->bbox[3] = c1;
+    p->Sr = r1 - r0 + 1;
+    p->Sc = c1 - c0 + 1;
+    const int S = p->Sr > p->Sc ? p->Sr : p->Sc;
+    int M = 16;
+    while (M < S - 1) M <<= 1;
+    if (M > N) M = N;
+    p->zp.L = N; p->zp.M = M; p->zp.R = N / M;
+    p->out.W = pn; p->out.center = pn / 2;
+    p->zp.Wr = (pn + p->zp.R - 1) / p->zp.R;
+    if (dispatch_shape(M, &p->rows_fpc, &p->cols_cb)) {
+        delete p;
+        return fail(LITHO_ERR_ARG, "plan_create: unsupported sub-FFT length");
+    }
+    // twiddle table in double precision on the host
+    std::vector<cplx> tw(N);
+    for (int i = 0; i < N; ++i) {
+        const double a = 2.0 * M_PI * (double)i / (double)N;
+        tw[i].x = (float)cos(a);
+        tw[i].y = (float)sin(a);
+    }
+    p->twL = nullptr;
+    int rc = be_malloc((void**)&p->twL, sizeof(cplx) * N);
+    if (rc == 0) rc = be_h2d(p->twL, tw.data(), sizeof(cplx) * N, 0);
+#if !defined(LITHO_EMU)
+    if (rc == 0) rc = (int)cudaStreamSynchronize(0);
+#endif
+    if (rc != 0) {
+        if (p->twL) be_free(p->twL);
+        delete p;
+        return fail(LITHO_ERR_CUDA, std::string("plan_create: ") + be_errstr(rc));
+    }
+    // batch: keep T for one launch pair around 64 MB (L2-resident on B200), at least 1, at most 16
+    const size_t per = (size_t)p->zp.R * p->Sr * p->zp.Wr * sizeof(cplx);
+    int b = (int)((64u << 20) / (per ? per : 1));
+    p->default_batch = b < 1 ? 1 : (b > 16 ? 16 : b);
+    *out = p;
+    return LITHO_OK;
+}
+
+void litho_plan_destroy(litho_plan_t* p) {
+    if (!p) return;
+    if (p->twL) be_free(p->twL);
+    delete p;
+}
+
+static uint64_t intensity_elems(const litho_plan* p) {
+    return (uint64_t)p->zp.R * p->zp.R * p->zp.Wr * p->zp.Wr;
+}
+
+int litho_plan_get_info(const litho_plan_t* p, litho_plan_info_t* info) {
+    if (!p || !info) return fail(LITHO_ERR_ARG, "plan_get_info: null argument");
+    info->pn = p->pn; info->N = p->N;
+    memcpy(info->bbox, p->bbox, sizeof(p->bbox));
+    info->L = p->zp.L; info->M = p->zp.M; info->R = p->zp.R; info->Wr = p->zp.Wr;
+    info->path = 1;
+    info->default_batch = p->default_batch;
+    info->intensity_elems = intensity_elems(p);
+    return LITHO_OK;
+}
+
+size_t litho_plan_workspace_bytes(const litho_plan_t* p, int batch) {
+    if (!p) return 0;
+    if (batch <= 0) batch = p->default_batch;
+    return (size_t)batch * p->zp.R * p->Sr * p->zp.Wr * sizeof(cplx);
+}
+
+static AxisIn axis_in(int first, int pn, int S) {
+    AxisIn a;
+    a.first = first; a.period = pn; a.center = pn / 2; a.S = S;
+    return a;
+}
+
+int litho_abbe_fft_accumulate(const litho_plan_t* p, const void* maskFT, const void* pupil, const int32_t* shifts,
+                              const float* weights, int n_src, int batch, float* intensity, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+    if (!p || !maskFT || !pupil || !intensity) return fail(LITHO_ERR_ARG, "accumulate: null argument");
+    if (n_src < 0) return fail(LITHO_ERR_ARG, "accumulate: negative n_src");
+    if (n_src == 0) return LITHO_OK;
+    if (!shifts) return fail(LITHO_ERR_ARG, "accumulate: shifts is null");
+    if (batch <= 0) batch = p->default_batch;
+    if (batch > n_src) batch = n_src;
+    if (!workspace || workspace_bytes < litho_plan_workspace_bytes(p, batch))
+        return fail(LITHO_ERR_WORKSPACE, "accumulate: workspace too small for the requested batch");
+    litho_stream_t st = (litho_stream_t)stream;
+    const int R = p->zp.R, M = p->zp.M;
+
+    RowsParams rp;
+    memset(&rp, 0, sizeof(rp));
+    rp.pupil = (const cplx*)pupil; rp.mask = (const cplx*)maskFT; rp.pn = p->pn;
+    rp.pr0 = p->bbox[0]; rp.pc0 = p->bbox[2];
+    rp.shifts = (const int2_*)shifts;
+    rp.lines = p->Sr;
+    rp.ax = axis_in(p->bbox[2], p->pn, p->Sc);
+    rp.out = p->out; rp.plan = p->zp; rp.twL = p->twL; rp.T = (cplx*)workspace;
+
+    ColsParams cp;
+    memset(&cp, 0, sizeof(cp));
+    cp.T = (const cplx*)workspace;
+    cp.Rc = R; cp.Wrc = p->zp.Wr; cp.outc = p->out;
+    cp.shifts = (const int2_*)shifts; cp.weights = weights;
+    cp.ax = axis_in(p->bbox[0], p->pn, p->Sr);
+    cp.out = p->out; cp.plan = p->zp; cp.twL = p->twL;
+    cp.iperm = intensity; cp.scale = 1.f;
+
+    const int gx_rows = (p->Sr * R + p->rows_fpc - 1) / p->rows_fpc;
+    const int gx_cols = R * ((p->zp.Wr + p->cols_cb - 1) / p->cols_cb);
+    for (int s0 = 0; s0 < n_src; s0 += batch) {
+        const int nb = (n_src - s0) < batch ? (n_src - s0) : batch;
+        rp.s_begin = s0;
+        BE_CHECK(dispatch_rows(M, ROW_PUPIL_MASK, rp, gx_rows, nb, st));
+        cp.s_begin = s0; cp.batch = nb;
+        BE_CHECK(dispatch_cols(M, EPI_ACCUM, cp, gx_cols, R, st));
+    }
+    return LITHO_OK;
+}
+
+static PermView perm_view(const litho_plan* p, const float* intensity) {
+    PermView v;
+    v.iperm = intensity;
+    v.outr = p->out; v.outc = p->out;
+    v.Rr = p->zp.R; v.Rc = p->zp.R; v.Wrr = p->zp.Wr; v.Wrc = p->zp.Wr;
+    return v;
+}
+
+// imageformation.py:71-75 size arithmetic (python semantics: floor, round-half-even, floor division)
+static void post_sizes(int pn, double eps, int* side, int* pW, int* out_side) {
+    const double sf = 1.0 / eps;
+    *side = (int)floor((double)pn * sf);
+    const long rnd = (long)nearbyint((double)pn / eps);
+    const long diff = (long)pn - rnd;
+    *pW = (int)(diff >= 0 ? diff / 2 : -((-diff + 1) / 2));
+    const int corr = *side % 2;
+    *out_side = *side + 2 * (*pW) + corr;
+}
+
+int litho_fft_output_side(int pn, double eps) {
+    int side, pW, os;
+    post_sizes(pn, eps, &side, &pW, &os);
+    return os;
+}
+
+int litho_abbe_fft_finalize(const litho_plan_t* p, const float* intensity, double eps, float* out, void* stream) {
+    if (!p || !intensity || !out || !(eps > 0)) return fail(LITHO_ERR_ARG, "finalize: bad argument");
+    FinalizeParams F;
+    F.in = perm_view(p, intensity);
+    F.pn = p->pn;
+    post_sizes(p->pn, eps, &F.side, &F.pW, &F.out_side);
+    if (F.out_side <= 0) return fail(LITHO_ERR_ARG, "finalize: empty output");
+    F.scale = (float)(1.0 / (1.0 / eps));
+    F.out = out;
+#if defined(LITHO_EMU)
+    (void)stream;
+    for (int y = 0; y < F.out_side; ++y)
+        for (int x = 0; x < F.out_side; ++x) finalize_pixel(F, y, x);
+#else
+    dim3 grid((F.out_side + 255) / 256, F.out_side, 1);
+    finalize_kernel<<<grid, 256, 0, (litho_stream_t)stream>>>(F);
+    BE_CHECK((int)cudaGetLastError());
+#endif
+    return LITHO_OK;
+}
+
+int litho_abbe_fft_unpermute(const litho_plan_t* p, const float* intensity, float* out, void* stream) {
+    if (!p || !intensity || !out) return fail(LITHO_ERR_ARG, "unpermute: null argument");
+    UnpermParams U;
+    U.in = perm_view(p, intensity);
+    U.pn = p->pn;
+    U.out = out;
+#if defined(LITHO_EMU)
+    (void)stream;
+    for (int y = 0; y < U.pn; ++y)
+        for (int x = 0; x < U.pn; ++x) out[(size_t)y * U.pn + x] = U.in.at(y, x);
+#else
+    dim3 grid((U.pn + 255) / 256, U.pn, 1);
+    unpermute_kernel<<<grid, 256, 0, (litho_stream_t)stream>>>(U);
+    BE_CHECK((int)cudaGetLastError());
+#endif
+    return LITHO_OK;
+}
+
+int litho_fft_field(const litho_plan_t* p, const void* pf, const void* maskFT, void* field, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+    if (!p || !pf || !maskFT || !field) return fail(LITHO_ERR_ARG, "fft_field: null argument");
+    if (!workspace || workspace_bytes < litho_plan_workspace_bytes(p, 1))
+        return fail(LITHO_ERR_WORKSPACE, "fft_field: workspace too small");
+    litho_stream_t st = (litho_stream_t)stream;
+    const int R = p->zp.R, M = p->zp.M;
+    RowsParams rp;
+    memset(&rp, 0, sizeof(rp));
+    rp.pupil = (const cplx*)pf; rp.mask = (const cplx*)maskFT; rp.pn = p->pn;
+    rp.pr0 = p->bbox[0]; rp.pc0 = p->bbox[2];
+    rp.shifts = nullptr;
+    rp.lines = p->Sr;
+    rp.ax = axis_in(p->bbox[2], p->pn, p->Sc);
+    rp.out = p->out; rp.plan = p->zp; rp.twL = p->twL; rp.T = (cplx*)workspace;
+    ColsParams cp;
+    memset(&cp, 0, sizeof(cp));
+    cp.T = (const cplx*)workspace;
+    cp.batch = 1;
+    cp.Rc = R; cp.Wrc = p->zp.Wr; cp.outc = p->out;
+    cp.ax = axis_in(p->bbox[0], p->pn, p->Sr);
+    cp.out = p->out; cp.plan = p->zp; cp.twL = p->twL;
+    cp.field = (cplx*)field; cp.field_pitch = p->pn; cp.conj_out = 0; cp.scale = 1.f;
+    const int gx_rows = (p->Sr * R + p->rows_fpc - 1) / p->rows_fpc;
+    const int gx_cols = R * ((p->zp.Wr + p->cols_cb - 1) / p->cols_cb);
+    BE_CHECK(dispatch_rows(M, ROW_PUPIL_MASK, rp, gx_rows, 1, st));
+    BE_CHECK(dispatch_cols(M, EPI_FIELD, cp, gx_cols, R, st));
+    return LITHO_OK;
+}
+
+}  // extern "C"
