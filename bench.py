@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""Headline benchmark: aerial images/s at 2048^2 x ~1k source points (BASELINE.json cfg3).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg3]
+
+One "step" = one full aerial image: abbeImage(fft=True) over all source points of the config
+(mask spectrum and pupil are inputs, as in the reference's call).  Prints ONE JSON line.
+
+  value        images/s with inputs resident in HBM, timed with CUDA events per step, L2 flushed
+               between steps, max over ranks.  N > 1: the source points are sharded across ranks and
+               the partial intensity planes are summed with one NCCL all-reduce per image, so the job
+               is ONE image computed N-way ("scaling": "strong").
+  e2e          same metric through the public API with HOST (pinned) tensors: H2D of mask spectrum,
+               pupil and source, compute, D2H of the image, all inside the timed region.
+  roofline     dominant kernel (column pass) timed alone with CUDA events on its stream; algorithmic
+               flops per SURVEY.md section 8d; FP32 peak measured in this run by an FMA probe.
+  cpu_baseline the oracle (numpy port of the reference algorithm) on a bounded sample of source
+               points on this box's host cores, extrapolated linearly in n_src (the loop is strictly
+               per source point, reference imageformation.py:62-67).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "aerial images/s at 2048^2 x 1k source pts"
+UNIT = "images/s"
+
+
+# ----------------------------------------------------------------------------- workload
+def build_inputs_host(cfg_name: str):
+    """Synthetic inputs of a BASELINE config, built on the host with the oracle builders (numpy)."""
+    from oracle import abbe_oracle as O
+    from lithographysimulator_b200 import workloads as wl
+    cfg = wl.CONFIGS[cfg_name]
+    geom = cfg.geometry()
+    mft = O.fraunhofer(geom, cfg.pixel_size, cfg.wavelength, True, np.complex128).astype(np.complex64)
+    if cfg.source == "quasar":
+        ls = O.light_source_quasar(cfg.sigma_in, cfg.sigma_out, cfg.pn, 4, -math.pi / 8)
+    else:
+        ls = O.light_source_annular(cfg.sigma_in, cfg.sigma_out, cfg.pn)
+    ls = (ls * wl.lattice(cfg.pn, cfg.stride)).astype(np.int64)
+    pf, _ = O.pupil_function(cfg.aberrations, cfg.pn, cfg.na, cfg.wavelength)
+    return cfg, mft, pf.astype(np.complex64), ls
+
+
+def algorithmic_flops(pn: int, N: int, n_src: int):
+    """W_pt = (S + pn)*5*N*log2(N) + 6*S^2 + 4*pn^2, S = pn/2+1."""
+    S = pn // 2 + 1
+    lg = math.log2(N)
+    rows = S * 5 * N * lg + 6 * S * S
+    cols = pn * 5 * N * lg + 4 * pn * pn
+    return dict(rows=rows * n_src, cols=cols * n_src, total=(rows + cols) * n_src, per_point=rows + cols)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- reference arm
+def oracle_image_sample(mft, pf, shifts, N, threads):
+    """|E_s|^2 summed over `shifts` with the oracle's FFT solver, source points spread over host threads."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import abbe_oracle as O
+    pn = mft.shape[0]
+
+    def work(chunk):
+        acc = np.zeros((pn, pn), dtype=np.float32)
+        for d0, d1 in chunk:
+            e = O.calculate_fft_aerial(np.roll(pf, (int(d0), int(d1)), axis=(0, 1)), mft, pn, N, np.complex64)
+            acc += (e.real ** 2 + e.imag ** 2)
+        return acc
+
+    chunks = [shifts[i::threads] for i in range(threads) if len(shifts[i::threads])]
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        parts = list(ex.map(work, chunks))
+    return sum(parts)
+
+
+def time_cpu_baseline(cfg, mft, pf, ls, n_sample, threads):
+    from oracle import abbe_oracle as O
+    shifts = O.source_shifts(ls, cfg.pn)
+    n_src = len(shifts)
+    _, N = O.calculate_epsilon_n(4 / cfg.pn, cfg.pixel_size, cfg.wavelength)
+    sample = shifts[:: max(1, n_src // n_sample)][:n_sample]
+    oracle_image_sample(mft, pf, sample[:threads], N, threads)  # warm-up (thread pool, FFT plans)
+    t0 = time.perf_counter()
+    oracle_image_sample(mft, pf, sample, N, threads)
+    dt = time.perf_counter() - t0
+    per_image = dt / len(sample) * n_src
+    return 1.0 / per_image, len(sample), n_src, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg, mft, pf, ls = build_inputs_host(args.config)
+    threads = os.cpu_count() or 1
+    n_sample = max(threads, min(args.ref_sample, 4 * threads))
+    vals = []
+    for _ in range(max(1, min(args.steps, 3))):
+        v, ns, n_src, dt = time_cpu_baseline(cfg, mft, pf, ls, n_sample, threads)
+        vals.append(v)
+    v = float(np.median(vals))
+    line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals), "warmup": 1,
+            "ms_per_step": 1000.0 / v, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "complex64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": f"{cfg.name}: {cfg.pn}^2 {cfg.mask} mask, {cfg.source} source {n_src} pts, N=2*pn, "
+                                   "Zernike-aberrated pupil, FFT-approximation solver"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"{ns} of {n_src} source points per step, extrapolated linearly in n_src; "
+                                       "oracle numpy port (pocketfft complex64), one source point per host thread"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import lithographysimulator_b200 as L
+    from lithographysimulator_b200 import _native
+    from lithographysimulator_b200.imaging import AbbeEngine, source_shifts, epsilon_n
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _native.device_lib()
+
+    cfg, mft_h, pf_h, ls_h = build_inputs_host(args.config)
+    pn = cfg.pn
+    eps, N = epsilon_n(4 / pn, cfg.pixel_size, cfg.wavelength)
+    mft_d = torch.from_numpy(mft_h).to(dev)
+    pf_d = torch.from_numpy(pf_h).to(dev)
+    ls_d = torch.from_numpy(ls_h).to(dev)
+    eng = AbbeEngine.get(dev)
+    shifts_all = source_shifts(ls_d, pn)
+    n_src = int(shifts_all.shape[0])
+    shifts_mine = shifts_all[rank::world].contiguous()  # interleaved shard: equal work per rank
+    plan = eng.plan(pn, N, eng.pupil_bbox(pf_d))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def reduce_fn(inten):
+        if world > 1:
+            dist.all_reduce(inten)
+
+    def one_image():
+        inten = eng.intensity_plane(plan)
+        eng.accumulate(plan, mft_d, pf_d, shifts_mine, inten, None, args.batch)
+        reduce_fn(inten)
+        return eng.finalize(plan, inten, eps)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        img = one_image()
+    barrier()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for a, b in ev:
+        flush.fill_(1)          # evict L2 between timed iterations (not timed)
+        a.record()
+        img = one_image()
+        b.record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms.item())
+    ms_per_step = ms / args.steps
+    value = 1000.0 / ms_per_step
+
+    # ---- per-kernel timing (live, CUDA events on the launching stream, after the timed region) ----
+    inten = eng.intensity_plane(plan)
+    n_mine = int(shifts_mine.shape[0])
+    batch = args.batch if args.batch > 0 else plan.default_batch
+    batch = max(1, min(batch, n_mine))
+    wsb = plan.workspace_bytes(batch)
+    ws = eng.workspace(wsb)
+    kern = {}
+    for name, phases in (("rows", 1), ("cols", 2)):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        a.record()
+        plan.accumulate(mft_d.data_ptr(), pf_d.data_ptr(), shifts_mine.data_ptr(), None, n_mine, batch,
+                        inten.data_ptr(), ws.data_ptr(), wsb, eng.stream(), phases=phases)
+        b.record()
+        torch.cuda.synchronize(dev)
+        launches = (n_mine + batch - 1) // batch
+        kern[name] = {"ms_total": a.elapsed_time(b), "launches": launches}
+
+    # ---- FP32 peak measured in this run (FMA probe) ----
+    probe_out = torch.zeros(4, dtype=torch.float32, device=dev)
+    import ctypes as C
+    fl = C.c_double()
+    nsm = torch.cuda.get_device_properties(dev).multi_processor_count
+    best = 0.0
+    for _ in range(3):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        lib.check(lib.litho_fp32_probe(probe_out.data_ptr(), nsm * 8, 20000, C.byref(fl), eng.stream()), "probe")
+        b.record()
+        torch.cuda.synchronize(dev)
+        best = max(best, fl.value / (a.elapsed_time(b) * 1e-3) / 1e12)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end through the public API with host (pinned) tensors ----
+    mft_p = torch.from_numpy(mft_h).pin_memory()
+    pf_p = torch.from_numpy(pf_h).pin_memory()
+    ls_mine_h = np.zeros_like(ls_h)
+    idx = np.argwhere(ls_h != 0)[rank::world]
+    ls_mine_h[idx[:, 0], idx[:, 1]] = 1
+    ls_p = torch.from_numpy(ls_mine_h).pin_memory()
+    side = plan.output_side(eps)
+    out_p = torch.empty((side, side), dtype=torch.float32).pin_memory()
+    mask_obj = None
+
+    def e2e_once():
+        img_d = eng.abbe_fft(mft_p, pf_p, ls_p, cfg.pixel_size, 4 / pn, cfg.wavelength, reduce_fn=reduce_fn,
+                             batch=args.batch)
+        out_p.copy_(img_d, non_blocking=True)
+        torch.cuda.synchronize(dev)
+
+    e2e_once()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 5))
+    for _ in range(e2e_steps):
+        e2e_once()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    h2d = mft_p.numel() * 8 + pf_p.numel() * 8 + ls_p.numel() * 8
+    d2h = out_p.numel() * 4
+
+    if rank == 0:
+        fl_alg = algorithmic_flops(pn, N, n_mine)
+        cols_ms = kern["cols"]["ms_total"] / kern["cols"]["launches"]
+        cols_flops = fl_alg["cols"] / kern["cols"]["launches"]
+        achieved = cols_flops / (cols_ms * 1e-3) / 1e12
+        peak_nominal = nsm * 128 * 2 * (clocks["sm_max_mhz"] or 1965.0) * 1e6 / 1e12
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        step_ach = algorithmic_flops(pn, N, n_src)["total"] / (ms_per_step * 1e-3) / 1e12
+        roofline = {
+            "bound": "fp32", "kernel": "abbe_cols_kernel (column pass + |E|^2 accumulate)",
+            "achieved": achieved, "peak": best, "unit": "TFLOP/s", "frac": achieved / best if best else None,
+            "peak_source": "FP32 FMA probe measured in this run (MEASURED_PEAKS.json has no FP32 entry); "
+                           f"nominal {peak_nominal:.1f} TFLOP/s = SMs*128*2*max clock",
+            "flops_per_launch": cols_flops, "ms_per_launch": cols_ms, "traffic": None,
+            "rows_kernel": {"achieved": (fl_alg["rows"] / kern["rows"]["launches"]) /
+                            (kern["rows"]["ms_total"] / kern["rows"]["launches"] * 1e-3) / 1e12,
+                            "ms_per_launch": kern["rows"]["ms_total"] / kern["rows"]["launches"]},
+            "whole_step": {"achieved": step_ach * 1.0, "frac": step_ach / best if best else None,
+                           "flops_per_image": algorithmic_flops(pn, N, n_src)["total"]},
+            "hbm": {"compulsory_bytes_per_image": 8 * pn * pn * 2 + 8 * n_src + 4 * pn * pn,
+                    "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
+        }
+        launches_per_step = 2 * ((n_mine + batch - 1) // batch) + 1
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            v, ns, _, dt = time_cpu_baseline(cfg, mft_h, pf_h, ls_h, max(threads, min(args.ref_sample, 4 * threads)),
+                                             threads)
+            cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"{ns} of {n_src} source points ({dt:.1f} s), extrapolated linearly in n_src; "
+                             "oracle numpy port, one source point per host thread"}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "complex64", "data": "synthetic",
+                "config": {"workload": f"{cfg.name}: {pn}^2 {cfg.mask} mask, {cfg.source} source {n_src} pts, N={N}, "
+                                       "Zernike-aberrated pupil, FFT-approximation solver",
+                           "l2": "flushed (256 MB write) between timed iterations", "batch": batch,
+                           "subfft": plan.M, "residues": plan.R, "sharding": f"source points interleaved over {world} rank(s), "
+                                                                           "one NCCL all-reduce of the intensity plane"},
+                "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
+                "e2e": {"value": 1.0 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "roofline": roofline, "cpu_baseline": cpu, "wall_s_timed_region": t_wall}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg3")
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--ref-sample", type=int, default=32)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -73,6 +73,14 @@ int litho_abbe_fft_accumulate(const litho_plan_t* plan, const void* maskFT, cons
                               const int32_t* shifts, const float* weights, int n_src, int batch,
                               float* intensity, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Same as litho_abbe_fft_accumulate with a phase mask for profiling: bit 0 = row pass, bit 1 = column
+ * pass (3 = both).  Running one pass alone re-uses whatever T holds, so results are only
+ * meaningful with both bits set; bench.py uses the single-pass forms to time each kernel live. */
+int litho_abbe_fft_accumulate_ex(const litho_plan_t* plan, const void* maskFT, const void* pupil,
+                                 const int32_t* shifts, const float* weights, int n_src, int batch,
+                                 float* intensity, void* workspace, size_t workspace_bytes, void* stream,
+                                 int phases);
+
 /* Post-processing of abbeImage(fft=True)                      imageformation.py:69-75
  * abs -> bilinear resample by 1/eps -> zero border; out has litho_fft_output_side(pn,eps)^2 floats. */
 int litho_fft_output_side(int pn, double eps);
@@ -86,6 +94,10 @@ int litho_abbe_fft_unpermute(const litho_plan_t* plan, const float* intensity, f
  * created from the bounding box of `pf`. */
 int litho_fft_field(const litho_plan_t* plan, const void* pf, const void* maskFT, void* field,
                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* FP32 FMA throughput probe (roofline denominator measured in the same run): launches `blocks` CTAs
+ * of 256 threads, each thread doing iters*16 dependent-chain FMAs; *flops receives the flop count. */
+int litho_fp32_probe(float* out, int blocks, int iters, double* flops, void* stream);
 
 #ifdef __cplusplus
 }

@@ -38,6 +38,8 @@ SYMBOLS = [
     ("litho_plan_get_info", C.c_int, [_P, C.POINTER(PlanInfo)]),
     ("litho_plan_workspace_bytes", C.c_size_t, [_P, C.c_int]),
     ("litho_abbe_fft_accumulate", C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P, C.c_size_t, _P]),
+    ("litho_abbe_fft_accumulate_ex", C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P, C.c_size_t, _P, C.c_int]),
+    ("litho_fp32_probe", C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_double), _P]),
     ("litho_fft_output_side", C.c_int, [C.c_int, C.c_double]),
     ("litho_abbe_fft_finalize", C.c_int, [_P, _P, C.c_double, _P, _P]),
     ("litho_abbe_fft_unpermute", C.c_int, [_P, _P, _P, _P]),
@@ -102,9 +104,10 @@ class Plan:
     def workspace_bytes(self, batch: int = 0) -> int:
         return int(self.lib.litho_plan_workspace_bytes(self.handle, batch))
 
-    def accumulate(self, maskFT, pupil, shifts, weights, n_src, batch, intensity, workspace, workspace_bytes, stream=0):
-        self.lib.check(self.lib.litho_abbe_fft_accumulate(self.handle, maskFT, pupil, shifts, weights, n_src, batch,
-                                                          intensity, workspace, workspace_bytes, stream),
+    def accumulate(self, maskFT, pupil, shifts, weights, n_src, batch, intensity, workspace, workspace_bytes, stream=0,
+                   phases=3):
+        self.lib.check(self.lib.litho_abbe_fft_accumulate_ex(self.handle, maskFT, pupil, shifts, weights, n_src, batch,
+                                                             intensity, workspace, workspace_bytes, stream, phases),
                        "litho_abbe_fft_accumulate")
 
     def output_side(self, eps: float) -> int:

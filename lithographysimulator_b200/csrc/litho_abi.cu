@@ -104,6 +104,20 @@ struct UnpermParams {
 };
 
 #if !defined(LITHO_EMU)
+__global__ void __launch_bounds__(256) fma_probe_kernel(float* out, int iters) {
+    float a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = (float)(threadIdx.x + i) * 1e-3f;
+    const float b = 0.999f, c = 1e-4f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] = fmaf(a[i], b, c);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += a[i];
+    if (s == 12345.678f) out[0] = s;  // never true: keeps the loop alive without memory traffic
+}
 __global__ void bbox_kernel(const __grid_constant__ BBoxParams P) { bbox_body(P, DevCtx{}); }
 __global__ void finalize_kernel(const __grid_constant__ FinalizeParams P) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -118,6 +132,47 @@ __global__ void unpermute_kernel(const __grid_constant__ UnpermParams P) {
 #endif
 
 }  // namespace litho
+
+// --------------------------------------------------------------------------- twiddle tables
+// w_L[i] = exp(+2*pi*i*i/L), computed in double on the host, one table per (device, L), kept for
+// the life of the process (at most 128 KB each).
+#include <map>
+#include <mutex>
+static std::mutex g_tw_mutex;
+static std::map<std::pair<int, int>, cplx*> g_tw_cache;
+
+static int get_twiddles(int L, cplx** out) {
+    int dev = 0;
+#if !defined(LITHO_EMU)
+    if (cudaGetDevice(&dev) != cudaSuccess) return 1;
+#endif
+    std::lock_guard<std::mutex> lock(g_tw_mutex);
+    auto key = std::make_pair(dev, L);
+    auto it = g_tw_cache.find(key);
+    if (it != g_tw_cache.end()) {
+        *out = it->second;
+        return 0;
+    }
+    std::vector<cplx> tw(L);
+    for (int i = 0; i < L; ++i) {
+        const double a = 2.0 * M_PI * (double)i / (double)L;
+        tw[i].x = (float)cos(a);
+        tw[i].y = (float)sin(a);
+    }
+    cplx* d = nullptr;
+    int rc = be_malloc((void**)&d, sizeof(cplx) * L);
+    if (rc == 0) rc = be_h2d(d, tw.data(), sizeof(cplx) * L, 0);
+#if !defined(LITHO_EMU)
+    if (rc == 0) rc = (int)cudaStreamSynchronize(0);
+#endif
+    if (rc != 0) {
+        if (d) be_free(d);
+        return rc;
+    }
+    g_tw_cache[key] = d;
+    *out = d;
+    return 0;
+}
 
 // --------------------------------------------------------------------------- plan
 struct litho_plan {
@@ -240,23 +295,11 @@ int litho_plan_create(int pn, int N, const int* bbox, int flags, litho_plan_t** 
         delete p;
         return fail(LITHO_ERR_ARG, "plan_create: unsupported sub-FFT length");
     }
-    // twiddle table in double precision on the host
-    std::vector<cplx> tw(N);
-    for (int i = 0; i < N; ++i) {
-        const double a = 2.0 * M_PI * (double)i / (double)N;
-        tw[i].x = (float)cos(a);
-        tw[i].y = (float)sin(a);
-    }
     p->twL = nullptr;
-    int rc = be_malloc((void**)&p->twL, sizeof(cplx) * N);
-    if (rc == 0) rc = be_h2d(p->twL, tw.data(), sizeof(cplx) * N, 0);
-#if !defined(LITHO_EMU)
-    if (rc == 0) rc = (int)cudaStreamSynchronize(0);
-#endif
+    int rc = get_twiddles(N, &p->twL);
     if (rc != 0) {
-        if (p->twL) be_free(p->twL);
         delete p;
-        return fail(LITHO_ERR_CUDA, std::string("plan_create: ") + be_errstr(rc));
+        return fail(LITHO_ERR_CUDA, std::string("plan_create: twiddle table: ") + be_errstr(rc));
     }
     // batch: keep T for one launch pair around 64 MB (L2-resident on B200), at least 1, at most 16
     const size_t per = (size_t)p->zp.R * p->Sr * p->zp.Wr * sizeof(cplx);
@@ -268,8 +311,7 @@ int litho_plan_create(int pn, int N, const int* bbox, int flags, litho_plan_t** 
 
 void litho_plan_destroy(litho_plan_t* p) {
     if (!p) return;
-    if (p->twL) be_free(p->twL);
-    delete p;
+    delete p;  // the twiddle table belongs to the process-wide cache
 }
 
 static uint64_t intensity_elems(const litho_plan* p) {
@@ -302,6 +344,13 @@ static AxisIn axis_in(int first, int pn, int S) {
 int litho_abbe_fft_accumulate(const litho_plan_t* p, const void* maskFT, const void* pupil, const int32_t* shifts,
                               const float* weights, int n_src, int batch, float* intensity, void* workspace,
                               size_t workspace_bytes, void* stream) {
+    return litho_abbe_fft_accumulate_ex(p, maskFT, pupil, shifts, weights, n_src, batch, intensity, workspace,
+                                        workspace_bytes, stream, 3);
+}
+
+int litho_abbe_fft_accumulate_ex(const litho_plan_t* p, const void* maskFT, const void* pupil, const int32_t* shifts,
+                                 const float* weights, int n_src, int batch, float* intensity, void* workspace,
+                                 size_t workspace_bytes, void* stream, int phases) {
     if (!p || !maskFT || !pupil || !intensity) return fail(LITHO_ERR_ARG, "accumulate: null argument");
     if (n_src < 0) return fail(LITHO_ERR_ARG, "accumulate: negative n_src");
     if (n_src == 0) return LITHO_OK;
@@ -336,9 +385,9 @@ int litho_abbe_fft_accumulate(const litho_plan_t* p, const void* maskFT, const v
     for (int s0 = 0; s0 < n_src; s0 += batch) {
         const int nb = (n_src - s0) < batch ? (n_src - s0) : batch;
         rp.s_begin = s0;
-        BE_CHECK(dispatch_rows(M, ROW_PUPIL_MASK, rp, gx_rows, nb, st));
+        if (phases & 1) BE_CHECK(dispatch_rows(M, ROW_PUPIL_MASK, rp, gx_rows, nb, st));
         cp.s_begin = s0; cp.batch = nb;
-        BE_CHECK(dispatch_cols(M, EPI_ACCUM, cp, gx_cols, R, st));
+        if (phases & 2) BE_CHECK(dispatch_cols(M, EPI_ACCUM, cp, gx_cols, R, st));
     }
     return LITHO_OK;
 }
@@ -434,6 +483,21 @@ int litho_fft_field(const litho_plan_t* p, const void* pf, const void* maskFT, v
     const int gx_cols = R * ((p->zp.Wr + p->cols_cb - 1) / p->cols_cb);
     BE_CHECK(dispatch_rows(M, ROW_PUPIL_MASK, rp, gx_rows, 1, st));
     BE_CHECK(dispatch_cols(M, EPI_FIELD, cp, gx_cols, R, st));
+    return LITHO_OK;
+}
+
+// FP32 FMA-throughput probe used by bench.py for the roofline denominator: every thread runs
+// `iters` rounds of 16 independent FMAs.  Returns the flop count of the launch in *flops.
+int litho_fp32_probe(float* out, int blocks, int iters, double* flops, void* stream) {
+    if (!out || blocks <= 0 || iters <= 0) return fail(LITHO_ERR_ARG, "fp32_probe: bad argument");
+    if (flops) *flops = (double)blocks * 256.0 * (double)iters * 16.0 * 2.0;
+#if defined(LITHO_EMU)
+    (void)stream;
+    out[0] = 0.f;
+#else
+    fma_probe_kernel<<<blocks, 256, 0, (litho_stream_t)stream>>>(out, iters);
+    BE_CHECK((int)cudaGetLastError());
+#endif
     return LITHO_OK;
 }
 

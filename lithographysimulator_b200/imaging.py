@@ -1,0 +1,178 @@
+"""Image formation: the reference's ``imageformation`` call surface on the B200-native kernels.
+
+Mirrors, by name and positional order:
+
+    abbeImage(mask, maskFT, pupilF, lightsource, pixelSize, deltaK, wavelength, fft, device)
+    calculateFFTAerial(pf, maskFFFT, pixelNumber, N)
+    calculateAerial(pupil, maskFT, fraunhoferConstant, pixelNumber, pixelSize, device)
+
+(reference imageformation.py:47, :32, :3).  The arithmetic runs in hand-written sm_100a CUDA
+behind the C ABI of include/litho_b200.h; torch is used for device memory and streams only.
+There is no CPU path: a non-CUDA device raises.
+"""
+from __future__ import annotations
+
+import threading
+
+import torch
+
+from . import _native
+
+__all__ = ["abbeImage", "calculateFFTAerial", "calculateAerial", "AbbeEngine", "source_shifts", "epsilon_n"]
+
+
+def _require_cuda(device) -> torch.device:
+    dev = torch.device(device) if device is not None else torch.device("cuda")
+    if dev.type != "cuda":
+        raise _native.LithoError(
+            f"lithographysimulator_b200 runs on CUDA devices only (got device={dev}); there is no CPU fallback")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+def epsilon_n(deltaK: float, pixelSize, wavelength: float):
+    """Mask.calculateEpsilonN (reference mask.py:63-72) evaluated on the host."""
+    return _native.device_lib().epsilon_n(float(deltaK), float(pixelSize), float(wavelength))
+
+
+def source_shifts(lightsource: torch.Tensor, pixelNumber: int) -> torch.Tensor:
+    """(argwhere(lightsource) - pn//2).int()  -- reference imageformation.py:59 (row-major order, values ignored)."""
+    return (torch.argwhere(lightsource) - (pixelNumber // 2)).to(torch.int32).contiguous()
+
+
+def _as_c64(t: torch.Tensor, dev: torch.device) -> torch.Tensor:
+    return t.to(device=dev, dtype=torch.complex64, non_blocking=True).contiguous()
+
+
+class AbbeEngine:
+    """Per-device cache of plans and workspaces for the FFT-approximation path."""
+
+    _engines: dict = {}
+    _lock = threading.Lock()
+
+    def __init__(self, device: torch.device):
+        self.device = device
+        self.lib = _native.device_lib()
+        self._plans: dict = {}
+        self._workspace: torch.Tensor | None = None
+
+    @classmethod
+    def get(cls, device) -> "AbbeEngine":
+        dev = _require_cuda(device)
+        with cls._lock:
+            eng = cls._engines.get(dev)
+            if eng is None:
+                eng = cls._engines[dev] = AbbeEngine(dev)
+            return eng
+
+    # -- helpers ---------------------------------------------------------------------------
+    def stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def pupil_bbox(self, pupil_d: torch.Tensor):
+        return self.lib.pupil_bbox(pupil_d.data_ptr(), pupil_d.shape[0], self.stream())
+
+    def plan(self, pn: int, N: int, bbox) -> _native.Plan:
+        key = (pn, N, tuple(bbox))
+        p = self._plans.get(key)
+        if p is None:
+            p = self._plans[key] = self.lib.plan_create(pn, N, bbox)
+        return p
+
+    def workspace(self, nbytes: int) -> torch.Tensor:
+        if self._workspace is None or self._workspace.numel() < nbytes:
+            self._workspace = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=self.device)
+        return self._workspace
+
+    # -- hot path --------------------------------------------------------------------------
+    def accumulate(self, plan: _native.Plan, maskFT_d, pupil_d, shifts_d, intensity, weights_d=None, batch: int = 0):
+        """intensity += sum_s w_s |IDFT{roll(P, shift_s) * M}|^2 (residue-major plane of `plan`)."""
+        n_src = int(shifts_d.shape[0])
+        if n_src == 0:
+            return
+        if batch <= 0:
+            batch = plan.default_batch
+        batch = min(batch, n_src)
+        wsb = plan.workspace_bytes(batch)
+        ws = self.workspace(wsb)
+        plan.accumulate(maskFT_d.data_ptr(), pupil_d.data_ptr(), shifts_d.data_ptr(),
+                        None if weights_d is None else weights_d.data_ptr(), n_src, batch,
+                        intensity.data_ptr(), ws.data_ptr(), wsb, self.stream())
+
+    def intensity_plane(self, plan: _native.Plan) -> torch.Tensor:
+        return torch.zeros(plan.intensity_elems, dtype=torch.float32, device=self.device)
+
+    def finalize(self, plan: _native.Plan, intensity: torch.Tensor, eps: float) -> torch.Tensor:
+        side = plan.output_side(eps)
+        out = torch.empty((side, side), dtype=torch.float32, device=self.device)
+        plan.finalize(intensity.data_ptr(), eps, out.data_ptr(), self.stream())
+        return out
+
+    def unpermute(self, plan: _native.Plan, intensity: torch.Tensor) -> torch.Tensor:
+        out = torch.empty((plan.pn, plan.pn), dtype=torch.float32, device=self.device)
+        plan.unpermute(intensity.data_ptr(), out.data_ptr(), self.stream())
+        return out
+
+    def abbe_fft(self, maskFT, pupilF, lightsource, pixelSize, deltaK, wavelength, *, weights=None, batch: int = 0,
+                 shifts=None, reduce_fn=None, postprocess: bool = True) -> torch.Tensor:
+        """abbeImage(fft=True).  `shifts` (int32 [n,2]) overrides the source-point extraction and
+        `reduce_fn(intensity)` runs between accumulation and post-processing (multi-GPU sum)."""
+        dev = self.device
+        with torch.cuda.device(dev):
+            maskFT_d = _as_c64(maskFT, dev)
+            pupil_d = _as_c64(pupilF, dev)
+            pn = maskFT_d.shape[0]
+            eps, N = epsilon_n(deltaK, pixelSize, wavelength)
+            if shifts is None:
+                ls_d = lightsource.to(dev, non_blocking=True)
+                shifts_d = source_shifts(ls_d, pn)
+            else:
+                shifts_d = shifts.to(device=dev, dtype=torch.int32).contiguous()
+            w_d = None if weights is None else weights.to(device=dev, dtype=torch.float32).contiguous()
+            plan = self.plan(pn, N, self.pupil_bbox(pupil_d))
+            intensity = self.intensity_plane(plan)
+            self.accumulate(plan, maskFT_d, pupil_d, shifts_d, intensity, w_d, batch)
+            if reduce_fn is not None:
+                reduce_fn(intensity)
+            return self.finalize(plan, intensity, eps) if postprocess else self.unpermute(plan, intensity)
+
+    def fft_field(self, pf, maskFT, pixelNumber: int, N: int) -> torch.Tensor:
+        dev = self.device
+        with torch.cuda.device(dev):
+            pf_d = _as_c64(pf, dev)
+            maskFT_d = _as_c64(maskFT, dev)
+            pn = maskFT_d.shape[0]
+            plan = self.plan(pn, int(N), self.pupil_bbox(pf_d))
+            wsb = plan.workspace_bytes(1)
+            ws = self.workspace(wsb)
+            field = torch.empty((pn, pn), dtype=torch.complex64, device=dev)
+            plan.fft_field(pf_d.data_ptr(), maskFT_d.data_ptr(), field.data_ptr(), ws.data_ptr(), wsb, self.stream())
+            return field
+
+
+def calculateFFTAerial(pf: torch.Tensor, maskFFFT: torch.Tensor, pixelNumber: int, N: int) -> torch.Tensor:
+    """Gau-2023 FFT-approximation field of one (already shifted) pupil -- reference imageformation.py:32-45."""
+    dev = maskFFFT.device if maskFFFT.is_cuda else (pf.device if pf.is_cuda else None)
+    return AbbeEngine.get(dev).fft_field(pf, maskFFFT, pixelNumber, N)
+
+
+def calculateAerial(pupil: torch.Tensor, maskFT: torch.Tensor, fraunhoferConstant, pixelNumber: int, pixelSize,
+                    device) -> torch.Tensor:
+    """Direct ("Abbe") solver field -- reference imageformation.py:3-30."""
+    from .direct import direct_field  # local import: separate kernel family
+    return direct_field(pupil, maskFT, fraunhoferConstant, pixelNumber, pixelSize, _require_cuda(device))
+
+
+def abbeImage(mask, maskFT: torch.Tensor, pupilF: torch.Tensor, lightsource: torch.Tensor, pixelSize, deltaK: float,
+              wavelength: float, fft: bool, device) -> torch.Tensor:
+    """Partially coherent aerial image by Abbe source-point summation -- reference imageformation.py:47-77.
+
+    Same arguments and result as the reference (float32 image on `device`); `mask` is accepted
+    for signature compatibility (the reference only uses it to reach calculateEpsilonN).
+    """
+    dev = _require_cuda(device)
+    if fft:
+        return AbbeEngine.get(dev).abbe_fft(maskFT, pupilF, lightsource, pixelSize, deltaK, wavelength)
+    from .direct import direct_abbe_image
+    return direct_abbe_image(maskFT, pupilF, lightsource, pixelSize, wavelength, dev)

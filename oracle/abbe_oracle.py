@@ -67,6 +67,18 @@ def _bilinear_axis(in_size: int, scale_factor: float):
     return out_size, i0, i1, l0, l1
 
 
+def pad2d(img: np.ndarray, lo: int, hi: int) -> np.ndarray:
+    """torch.nn.functional.pad(img, (lo, hi, lo, hi)): positive widths add zeros, negative widths crop."""
+    n = img.shape[0]
+    osz = max(n + lo + hi, 0)
+    res = np.zeros((osz, osz), dtype=img.dtype)
+    a = max(0, -lo)            # first source index kept
+    b = min(n, osz - lo)       # one past the last source index kept
+    if b > a:
+        res[a + lo:b + lo, a + lo:b + lo] = img[a:b, a:b]
+    return res
+
+
 def bilinear_resize(img: np.ndarray, scale_factor: float, dtype=F32) -> np.ndarray:
     """Square 2-D bilinear resample with torch semantics (same factor on both axes)."""
     img = np.asarray(img, dtype=dtype)
@@ -104,8 +116,7 @@ def ff_fraunhofer(geometry: np.ndarray, epsilon: float, N: int, cdtype=np.comple
     sm = scaled.shape[0]
     pW = ((N - pn) - (sm - pn)) // 2
     corr = sm % 2
-    padded = np.zeros((sm + 2 * pW + corr,) * 2, dtype=fdt)
-    padded[pW:pW + sm, pW:pW + sm] = scaled
+    padded = pad2d(scaled, pW, pW + corr)
     spec = np.fft.ifftshift(np.fft.fft2(np.fft.fftshift(padded).astype(cdtype)))
     trim = (N - pn) // 2
     return spec[trim:spec.shape[0] - trim, trim:spec.shape[1] - trim].astype(cdtype)
@@ -319,11 +330,7 @@ def fft_postprocess(image: np.ndarray, pn: int, epsilon: float, dtype=F32) -> np
     out = bilinear_resize(image, 1 / epsilon, dtype=dtype)
     pW = (pn - round(pn / epsilon)) // 2
     corr = out.shape[0] % 2
-    if pW < 0:  # torch.nn.functional.pad with negative width crops
-        raise ValueError("negative pad not supported by the oracle")
-    res = np.zeros((out.shape[0] + 2 * pW + corr,) * 2, dtype=dtype)
-    res[pW:pW + out.shape[0], pW:pW + out.shape[1]] = out
-    return res
+    return pad2d(out, pW, pW + corr)
 
 
 def abbe_image(maskFT: np.ndarray, pupilF: np.ndarray, lightsource: np.ndarray, pixelSize, deltaK: float,

@@ -1,0 +1,75 @@
+"""Runs the CUDA kernel bodies thread-for-thread on the CPU (tests/emu) through the C ABI and
+checks them against the reference goldens and the oracle.  This validates the index arithmetic
+of the device code without a GPU; it is not a product path (the product loads the sm_100a
+library only and has no CPU fallback)."""
+import numpy as np
+import pytest
+
+import helpers as H
+from oracle import abbe_oracle as O
+
+KAT = H.load_kat()
+
+
+@pytest.mark.parametrize("name", ["demo64_quasar", "ps50_64", "ps12_64", "np2_96", "wrap_128", "shifted_128",
+                                  "dense_64"])
+def test_emu_fft_image_matches_reference(name):
+    c = KAT[name]
+    img, info = H.emu_abbe_fft(c["maskFT"], c["pupil"], c["lightsource"], float(c["pixel_size"]), 193.0)
+    assert img.shape == c["image"].shape
+    assert O.rel_l2(img, c["image"]) < H.TOL
+
+
+def test_emu_batching_weights_and_empty_source():
+    c = KAT["demo64_quasar"]
+    shifts = O.source_shifts(c["lightsource"], 64)[:23]
+    rng = np.random.default_rng(0)
+    w = rng.uniform(0.5, 2.0, len(shifts)).astype(np.float32)
+    a, _ = H.emu_abbe_fft(c["maskFT"], c["pupil"], None, 25.0, 193.0, batch=1, weights=w, shifts=shifts, postprocess=False)
+    b, _ = H.emu_abbe_fft(c["maskFT"], c["pupil"], None, 25.0, 193.0, batch=7, weights=w, shifts=shifts, postprocess=False)
+    assert O.rel_l2(a, b) < 1e-6
+    ref = np.zeros((64, 64))
+    for (d0, d1), wi in zip(shifts, w):
+        e = O.calculate_fft_aerial(np.roll(c["pupil"], (d0, d1), (0, 1)), c["maskFT"], 64, 128)
+        ref += wi * np.abs(e) ** 2
+    assert O.rel_l2(a, ref) < H.TOL
+    z, _ = H.emu_abbe_fft(c["maskFT"], c["pupil"], np.zeros((64, 64), np.int64), 25.0, 193.0)
+    assert z.shape == (64, 64) and not z.any()
+
+
+def test_emu_complex_field():
+    f = KAT["field_fft_64"]
+    lib = H.emu_lib()
+    pf = np.ascontiguousarray(f["pf"])
+    mft = np.ascontiguousarray(f["maskFT"])
+    plan = lib.plan_create(64, 128, lib.pupil_bbox(pf.ctypes.data, 64))
+    wsb = plan.workspace_bytes(1)
+    ws = np.zeros(wsb, np.uint8)
+    field = np.zeros((64, 64), np.complex64)
+    plan.fft_field(pf.ctypes.data, mft.ctypes.data, field.ctypes.data, ws.ctypes.data, wsb)
+    assert np.linalg.norm(field - f["field"]) / np.linalg.norm(f["field"]) < H.TOL
+
+
+def test_emu_larger_subfft_sizes():
+    """One source point through M = 128 / 256 (three radix passes are exercised by M >= 512 on the GPU)."""
+    rng = np.random.default_rng(3)
+    for pn, box in ((256, (64, 192)), (256, (10, 250))):
+        pup = np.zeros((pn, pn), np.complex64)
+        lo, hi = box
+        n = hi - lo + 1
+        pup[lo:hi + 1, lo:hi + 1] = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+        mft = (rng.standard_normal((pn, pn)) + 1j * rng.standard_normal((pn, pn))).astype(np.complex64)
+        shifts = np.array([[3, -5]], np.int32)
+        img, info = H.emu_abbe_fft(mft, pup, None, 25.0, 193.0, shifts=shifts, postprocess=False)
+        e = O.calculate_fft_aerial(np.roll(pup, (3, -5), (0, 1)), mft, pn, 512)
+        assert O.rel_l2(img, np.abs(e) ** 2) < H.TOL, info
+
+
+def test_emu_rejects_unsupported():
+    lib = H.emu_lib()
+    with pytest.raises(Exception):
+        lib.plan_create(63, 128, (0, 62, 0, 62))       # odd grid
+    with pytest.raises(Exception):
+        lib.plan_create(256, 128, (0, 255, 0, 255))    # N < pn: the reference raises too (Q7)
+    with pytest.raises(Exception):
+        lib.plan_create(64, 100, (0, 63, 0, 63))       # N not a power of two

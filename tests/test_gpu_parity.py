@@ -1,0 +1,207 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA path, called through the
+reference-shaped Python API / C ABI, against (a) goldens produced by the reference itself and
+(b) the oracle on the same seeded inputs.  Tolerance: relative L2 <= 1e-5 on the aerial image
+(BASELINE.json north star).  Nothing here reads /root/reference."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+from oracle import abbe_oracle as O
+from lithographysimulator_b200 import workloads as wl
+
+pytestmark = pytest.mark.gpu
+
+KAT = H.load_kat()
+FFT_CASES = ["demo64_quasar", "demo64_annular", "ps50_64", "ps12_64", "np2_96", "wrap_128", "shifted_128", "dense_64"]
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def L(dev):
+    import lithographysimulator_b200 as L
+    from lithographysimulator_b200 import _native
+    lib = _native.device_lib()  # raises if liblitho_b200.so is missing: no fallback
+    assert lib.litho_is_device_build() == 1
+    return L
+
+
+def _t(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def _mask_stub(L, pn, ps, dev):
+    return L.Mask(torch.zeros((pn, pn), dtype=torch.int16), ps, dev)
+
+
+@pytest.mark.parametrize("name", FFT_CASES)
+def test_abbe_fft_matches_reference_golden(L, dev, name):
+    c = KAT[name]
+    pn = c["maskFT"].shape[0]
+    ps = int(c["pixel_size"])
+    m = _mask_stub(L, pn, ps, dev)
+    img = L.abbeImage(m, _t(c["maskFT"], dev), _t(c["pupil"], dev), _t(c["lightsource"], dev), ps, m.deltaK, 193.0,
+                      True, dev)
+    assert img.dtype == torch.float32 and tuple(img.shape) == c["image"].shape
+    assert O.rel_l2(img.cpu().numpy(), c["image"]) < H.TOL
+
+
+def test_abbe_fft_accepts_host_tensors(L, dev):
+    """The reference lets every argument live anywhere; host tensors are uploaded inside the call."""
+    c = KAT["demo64_quasar"]
+    m = _mask_stub(L, 64, 25, dev)
+    img = L.abbeImage(m, torch.from_numpy(c["maskFT"]), torch.from_numpy(c["pupil"]),
+                      torch.from_numpy(c["lightsource"]), 25, m.deltaK, 193.0, True, dev)
+    assert O.rel_l2(img.cpu().numpy(), c["image"]) < H.TOL
+
+
+def test_fft_field_matches_reference_golden(L, dev):
+    f = KAT["field_fft_64"]
+    e = L.calculateFFTAerial(_t(f["pf"], dev), _t(f["maskFT"], dev), 64, 128).cpu().numpy()
+    assert e.dtype == np.complex64
+    assert np.linalg.norm(e - f["field"]) / np.linalg.norm(f["field"]) < H.TOL
+
+
+def test_cpu_device_is_rejected(L):
+    c = KAT["demo64_quasar"]
+    with pytest.raises(Exception):
+        L.abbeImage(None, torch.from_numpy(c["maskFT"]), torch.from_numpy(c["pupil"]),
+                    torch.from_numpy(c["lightsource"]), 25, 4 / 64, 193.0, True, torch.device("cpu"))
+
+
+def test_empty_source_and_empty_pupil(L, dev):
+    c = KAT["demo64_quasar"]
+    m = _mask_stub(L, 64, 25, dev)
+    z = L.abbeImage(m, _t(c["maskFT"], dev), _t(c["pupil"], dev), torch.zeros((64, 64), dtype=torch.int64, device=dev),
+                    25, m.deltaK, 193.0, True, dev)
+    assert tuple(z.shape) == (64, 64) and float(z.abs().max()) == 0.0
+    z = L.abbeImage(m, _t(c["maskFT"], dev), torch.zeros((64, 64), dtype=torch.complex64, device=dev),
+                    _t(c["lightsource"], dev), 25, m.deltaK, 193.0, True, dev)
+    assert float(z.abs().max()) == 0.0
+
+
+def _cfg_inputs(name):
+    """Inputs of a BASELINE config from the oracle builders (pinned against the reference in the CPU suite)."""
+    cfg = wl.CONFIGS[name]
+    geom = cfg.geometry()
+    mft = O.fraunhofer(geom, cfg.pixel_size, cfg.wavelength, True, np.complex128).astype(np.complex64)
+    if cfg.source == "quasar":
+        ls = O.light_source_quasar(cfg.sigma_in, cfg.sigma_out, cfg.pn, 4, -math.pi / 8)
+    else:
+        ls = O.light_source_annular(cfg.sigma_in, cfg.sigma_out, cfg.pn)
+    ls = ls * wl.lattice(cfg.pn, cfg.stride)
+    pf, _ = O.pupil_function(cfg.aberrations, cfg.pn, cfg.na, cfg.wavelength)
+    return cfg, mft, pf, ls
+
+
+def test_cfg1_full_image(L, dev, golden_dir):
+    z = np.load(f"{golden_dir}/cfg1.npz")
+    cfg = wl.CONFIGS["cfg1"]
+    m = _mask_stub(L, cfg.pn, cfg.pixel_size, dev)
+    ls = O.light_source_annular(cfg.sigma_in, cfg.sigma_out, cfg.pn) * wl.lattice(cfg.pn, cfg.stride)
+    img = L.abbeImage(m, _t(z["maskFT"], dev), _t(z["pupil"], dev), _t(ls, dev), cfg.pixel_size, m.deltaK,
+                      cfg.wavelength, True, dev).cpu().numpy()
+    assert O.rel_l2(img, z["image"]) < H.TOL
+    # float64 reference run (north star): same inputs through the oracle in complex128
+    ref64 = O.abbe_image(z["maskFT"], z["pupil"], ls, cfg.pixel_size, 4 / cfg.pn, cfg.wavelength, True, np.complex128)
+    assert O.rel_l2(img, ref64) < H.TOL
+
+
+@pytest.mark.parametrize("name", ["cfg2", "cfg3"])
+def test_large_config_against_reference_sample(L, dev, golden_dir, name):
+    """Full-size BASELINE configs: every 16th pixel of the reference's own image plus its moments."""
+    z = np.load(f"{golden_dir}/{name}.npz")
+    cfg, mft, pf, ls = _cfg_inputs(name)
+    assert int((ls != 0).sum()) == int(z["n_src"])
+    # the oracle-built inputs agree with the reference-built ones at the sampled positions
+    st = int(z["sample_stride"])
+    assert np.linalg.norm(mft[::st, ::st] - z["maskFT_sample"]) / np.linalg.norm(z["maskFT_sample"]) < 1e-6
+    assert np.abs(pf[::st, ::st] - z["pupil_sample"]).max() < 1e-3
+    m = _mask_stub(L, cfg.pn, cfg.pixel_size, dev)
+    img = L.abbeImage(m, _t(mft, dev), _t(pf, dev), _t(ls, dev), cfg.pixel_size, m.deltaK, cfg.wavelength, True, dev)
+    img = img.cpu().numpy()
+    assert tuple(img.shape) == tuple(z["shape"])
+    assert O.rel_l2(img[::st, ::st], z["image_sample"]) < H.TOL
+    assert abs(img.sum(dtype=np.float64) / float(z["img_sum"]) - 1) < 1e-5
+    assert abs((img.astype(np.float64) ** 2).sum() / float(z["img_sumsq"]) - 1) < 2e-5
+
+
+def test_source_additivity_and_weights_full_size(L, dev):
+    """Size-independent properties at the headline grid (2048 px): I(S1 u S2) = I(S1) + I(S2) -- what licenses
+    sharding source points across GPUs -- and integer weights == repeated source points."""
+    from lithographysimulator_b200.imaging import AbbeEngine
+    cfg, mft, pf, ls = _cfg_inputs("cfg3")
+    eng = AbbeEngine.get(dev)
+    sh = torch.from_numpy(O.source_shifts(ls, cfg.pn))[:48]
+    mft_d, pf_d = _t(mft, dev), _t(pf, dev)
+    kw = dict(pixelSize=cfg.pixel_size, deltaK=4 / cfg.pn, wavelength=cfg.wavelength, postprocess=False)
+    full = eng.abbe_fft(mft_d, pf_d, None, shifts=sh, **kw)
+    a = eng.abbe_fft(mft_d, pf_d, None, shifts=sh[0::2], **kw)
+    b = eng.abbe_fft(mft_d, pf_d, None, shifts=sh[1::2], batch=5, **kw)
+    assert O.rel_l2((a + b).cpu().numpy(), full.cpu().numpy()) < 1e-6
+    w = torch.ones(48)
+    w[::3] = 2.0
+    weighted = eng.abbe_fft(mft_d, pf_d, None, shifts=sh, weights=w, **kw)
+    rep = eng.abbe_fft(mft_d, pf_d, None, shifts=torch.cat([sh, sh[::3]]), **kw)
+    assert O.rel_l2(weighted.cpu().numpy(), rep.cpu().numpy()) < 1e-6
+    # and one source point against the oracle's float64 field at full size
+    one = eng.abbe_fft(mft_d, pf_d, None, shifts=sh[7:8], **kw).cpu().numpy()
+    d0, d1 = (int(v) for v in sh[7])
+    e = O.calculate_fft_aerial(np.roll(pf, (d0, d1), (0, 1)), mft, cfg.pn, 4096)
+    assert O.rel_l2(one, np.abs(e) ** 2) < H.TOL
+
+
+@pytest.mark.parametrize("pn,box", [(512, (100, 400)), (1024, (256, 768)), (1024, (0, 1023))])
+def test_subfft_sizes_three_passes(L, dev, pn, box):
+    """Random dense windows that force sub-FFT lengths 512 / 512 / 1024 (three radix passes)."""
+    from lithographysimulator_b200.imaging import AbbeEngine
+    rng = np.random.default_rng(pn + box[0])
+    lo, hi = box
+    n = hi - lo + 1
+    pup = np.zeros((pn, pn), np.complex64)
+    pup[lo:hi + 1, lo:hi + 1] = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    mft = (rng.standard_normal((pn, pn)) + 1j * rng.standard_normal((pn, pn))).astype(np.complex64)
+    sh = torch.tensor([[7, -11], [-3, 2]], dtype=torch.int32)
+    eng = AbbeEngine.get(dev)
+    img = eng.abbe_fft(_t(mft, dev), _t(pup, dev), None, 25, 4 / pn, 193.0, shifts=sh, postprocess=False).cpu().numpy()
+    ref = np.zeros((pn, pn))
+    for d0, d1 in sh.numpy():
+        ref += np.abs(O.calculate_fft_aerial(np.roll(pup, (d0, d1), (0, 1)), mft, pn, 2 * pn)) ** 2
+    assert O.rel_l2(img, ref) < H.TOL
+
+
+def test_builders_match_oracle(L, dev):
+    cfg = wl.CONFIGS["cfg1"]
+    src = L.LightSource(0.4, 0.8, 256, 0.7, 0, 0, dev)
+    assert (src.generateQuasar(4, -math.pi / 8).cpu().numpy() == O.light_source_quasar(0.4, 0.8, 256, 4, -math.pi / 8)).all()
+    assert (src.generateAnnular().cpu().numpy() == O.light_source_annular(0.4, 0.8, 256)).all()
+    ab = torch.tensor(wl.ABERR_FULL, dtype=torch.float16, device=dev)
+    pf = L.Pupil(256, 193.0, 0.7, ab, dev).generatePupilFunction().cpu().numpy()
+    ref, ab_ref = O.pupil_function(wl.ABERR_FULL, 256, 0.7, 193.0)
+    assert ((pf != 0) == (ref != 0)).all()
+    assert np.linalg.norm(pf - ref) / np.linalg.norm(ref) < 1e-5
+    assert float(ab[4]) == float(ab_ref[4])  # in-place defocus rescale, like the reference (Q4)
+    m = L.Mask(torch.from_numpy(cfg.geometry()), 25, dev)
+    mft = m.fraunhofer(193.0, True).cpu().numpy()
+    ref = O.fraunhofer(cfg.geometry(), 25, 193.0, True)
+    assert np.linalg.norm(mft - ref) / np.linalg.norm(ref) < H.TOL
+
+
+def test_end_to_end_object_api(L, dev):
+    """The reference demo (imageformation.py:99-119) through the object API, against its golden image."""
+    c = KAT["demo64_quasar"]
+    m = L.Mask(device=dev, pixelSize=25)
+    mft = m.fraunhofer(193.0, True)
+    src = L.LightSource(sigmaIn=0.4, sigmaOut=0.8, device=dev)
+    ls = src.generateQuasar(4, -math.pi / (4 * 2))
+    ab = torch.tensor(wl.ABERR_FULL, dtype=torch.float16, device=dev)
+    pf = L.Pupil(m.pixelNumber, 193.0, src.NA, ab, device=dev).generatePupilFunction()
+    img = L.abbeImage(m, mft, pf, ls, m.pixelSize, m.deltaK, 193.0, True, dev).cpu().numpy()
+    assert O.rel_l2(img, c["image"]) < H.TOL
