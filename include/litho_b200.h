@@ -95,6 +95,30 @@ int litho_abbe_fft_unpermute(const litho_plan_t* plan, const float* intensity, f
 int litho_fft_field(const litho_plan_t* plan, const void* pf, const void* maskFT, void* field,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* Mask._ffFraunhofer(epsilon, N)                                    mask.py:74-90
+ * mask spectrum by the FFT approximation: geometry (pn x pn int16) -> bilinear upsample by eps ->
+ * centre-pad to N -> centred forward DFT -> crop; maskFT receives pn x pn complex64. */
+size_t litho_mask_spectrum_workspace_bytes(int pn, double eps, int N);
+int litho_mask_spectrum(const int16_t* geometry, int pn, double eps, int N, void* maskFT, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
+/* ---- direct ("Abbe") solver: E = A * G * A^T with the fp16-quantised phase table ----
+ * litho_direct_operator builds A[a][c] = w[c] * exp(sign*i*(2*pi/lambda)*fp16(fp16(k[a])*fp16(x[c])))
+ * (pn x pn complex64): sign = -1 for imaging (imageformation.py:52), +1 for the mask spectrum (mask.py:42). */
+int litho_direct_operator(int pn, double pixelSize, double wavelength, int sign, void* A, void* stream);
+size_t litho_direct_workspace_bytes(int pn, const int* bbox, int batch);
+/* abbeImage(fft=False) hot loop                                 imageformation.py:59-65 with :3-30
+ *   intensity[pn][pn] += sum_s w_s | A (roll(pupil, shift_s) * maskFT) A^T |^2   (natural row-major order) */
+int litho_direct_accumulate(const void* A, const void* maskFT, const void* pupil, int pn, const int* bbox,
+                            const int32_t* shifts, const float* weights, int n_src, int batch, float* intensity,
+                            void* workspace, size_t workspace_bytes, void* stream);
+/* calculateAerial(pupil, maskFT, ...)                            imageformation.py:3-30 */
+int litho_direct_field(const void* A, const void* pupil, const void* maskFT, int pn, const int* bbox, void* field,
+                       void* workspace, size_t workspace_bytes, void* stream);
+/* Mask.fraunhofer(wavelength, fft=False)                         mask.py:41-61  (A built with sign = +1) */
+int litho_direct_mask_spectrum(const void* Aplus, const int16_t* geometry, int pn, void* maskFT, void* workspace,
+                               size_t workspace_bytes, void* stream);
+
 /* FP32 FMA throughput probe (roofline denominator measured in the same run): launches `blocks` CTAs
  * of 256 threads, each thread doing iters*16 dependent-chain FMAs; *flops receives the flop count. */
 int litho_fp32_probe(float* out, int blocks, int iters, double* flops, void* stream);

@@ -39,6 +39,14 @@ SYMBOLS = [
     ("litho_plan_workspace_bytes", C.c_size_t, [_P, C.c_int]),
     ("litho_abbe_fft_accumulate", C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P, C.c_size_t, _P]),
     ("litho_abbe_fft_accumulate_ex", C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P, C.c_size_t, _P, C.c_int]),
+    ("litho_mask_spectrum_workspace_bytes", C.c_size_t, [C.c_int, C.c_double, C.c_int]),
+    ("litho_mask_spectrum", C.c_int, [_P, C.c_int, C.c_double, C.c_int, _P, _P, C.c_size_t, _P]),
+    ("litho_direct_operator", C.c_int, [C.c_int, C.c_double, C.c_double, C.c_int, _P, _P]),
+    ("litho_direct_workspace_bytes", C.c_size_t, [C.c_int, C.POINTER(C.c_int), C.c_int]),
+    ("litho_direct_accumulate", C.c_int, [_P, _P, _P, C.c_int, C.POINTER(C.c_int), _P, _P, C.c_int, C.c_int, _P, _P,
+                                          C.c_size_t, _P]),
+    ("litho_direct_field", C.c_int, [_P, _P, _P, C.c_int, C.POINTER(C.c_int), _P, _P, C.c_size_t, _P]),
+    ("litho_direct_mask_spectrum", C.c_int, [_P, _P, C.c_int, _P, _P, C.c_size_t, _P]),
     ("litho_fp32_probe", C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_double), _P]),
     ("litho_fft_output_side", C.c_int, [C.c_int, C.c_double]),
     ("litho_abbe_fft_finalize", C.c_int, [_P, _P, C.c_double, _P, _P]),

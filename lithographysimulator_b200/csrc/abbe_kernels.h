@@ -258,6 +258,31 @@ LITHO_HD void bilinear_src(float scale, int dst, int in_size, int& i0, int& i1, 
     l0 = 1.f - l1;
 }
 
+// mask.py:76-77: int16 geometry -> float32, bilinear resample by eps (same ATen rules as above)
+struct ResampleParams {
+    const int16_t* in;  // [pn][pn]
+    int pn;
+    int side;     // floor(pn * eps)
+    float scale;  // float32(1 / eps)
+    float* out;   // [side][side]
+};
+
+LITHO_HD void resample_pixel(const ResampleParams& P, int y, int x) {
+    float val;
+    if (P.side == P.pn) {
+        val = (float)P.in[(size_t)y * P.pn + x];
+    } else {
+        int r0, r1, c0, c1;
+        float lh0, lh1, lw0, lw1;
+        bilinear_src(P.scale, y, P.pn, r0, r1, lh0, lh1);
+        bilinear_src(P.scale, x, P.pn, c0, c1, lw0, lw1);
+        const float a = (float)P.in[(size_t)r0 * P.pn + c0], b = (float)P.in[(size_t)r0 * P.pn + c1];
+        const float c = (float)P.in[(size_t)r1 * P.pn + c0], d = (float)P.in[(size_t)r1 * P.pn + c1];
+        val = lh0 * (lw0 * a + lw1 * b) + lh1 * (lw0 * c + lw1 * d);
+    }
+    P.out[(size_t)y * P.side + x] = val;
+}
+
 LITHO_HD void finalize_pixel(const FinalizeParams& P, int y, int x) {
     float val = 0.f;
     const int yy = y - P.pW, xx = x - P.pW;

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "launch.h"
+#include "direct_kernels.h"
 
 #if defined(LITHO_EMU)
 #include "emu_runtime.h"
@@ -123,6 +124,25 @@ __global__ void finalize_kernel(const __grid_constant__ FinalizeParams P) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
     if (x < P.out_side) finalize_pixel(P, y, x);
+}
+__global__ void direct_op_kernel(const __grid_constant__ DirectOpParams P) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < P.pn) direct_op_elem(P, blockIdx.y, c);
+}
+template <int KIND>
+__global__ void __launch_bounds__(DIRECT_THREADS) direct_rows_kernel(const __grid_constant__ DirectParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    direct_rows_body<KIND>(P, DevCtx{}, reinterpret_cast<cplx*>(smem_raw));
+}
+template <int EPI>
+__global__ void __launch_bounds__(DIRECT_THREADS) direct_cols_kernel(const __grid_constant__ DirectParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    direct_cols_body<EPI>(P, DevCtx{}, reinterpret_cast<cplx*>(smem_raw));
+}
+__global__ void resample_kernel(const __grid_constant__ ResampleParams P) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x < P.side) resample_pixel(P, y, x);
 }
 __global__ void unpermute_kernel(const __grid_constant__ UnpermParams P) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -483,6 +503,226 @@ int litho_fft_field(const litho_plan_t* p, const void* pf, const void* maskFT, v
     const int gx_cols = R * ((p->zp.Wr + p->cols_cb - 1) / p->cols_cb);
     BE_CHECK(dispatch_rows(M, ROW_PUPIL_MASK, rp, gx_rows, 1, st));
     BE_CHECK(dispatch_cols(M, EPI_FIELD, cp, gx_cols, R, st));
+    return LITHO_OK;
+}
+
+// ---------------------------------------------------------------------------- mask spectrum
+// Mask._ffFraunhofer (mask.py:74-90): bilinear upsample of the int16 geometry by eps, centre-pad
+// to N, centred forward DFT, crop to pn.  The forward transform of a real plane is the conjugate
+// of the inverse one, so the imaging kernels are reused with a conjugating epilogue.
+struct SpecGeom {
+    int pn, N, sm;      // grid, transform length, resampled side
+    int u0, S, first;   // first resampled sample used, how many, and its position in the N grid
+    ZoomPlan zp;
+    AxisOut out;
+    int rows_fpc, cols_cb;
+    size_t plane_elems, t_elems;
+};
+
+static int spec_geom(int pn, double eps, int N, SpecGeom* g) {
+    if (pn < 2 || (pn & 1)) return 1;
+    if (!is_pow2(N) || N > 16384 || N < 16 || N < pn) return 1;
+    if (!(eps > 0)) return 1;
+    g->pn = pn; g->N = N;
+    g->sm = (int)floor((double)pn * eps);
+    if (g->sm < 1) return 1;
+    const long d = (long)(N - pn) - (long)(g->sm - pn);
+    const long pW = d >= 0 ? d / 2 : -((-d + 1) / 2);  // python floor division
+    g->u0 = pW < 0 ? (int)(-pW) : 0;                   // negative pad = crop (F.pad semantics)
+    g->first = pW < 0 ? 0 : (int)pW;
+    int S = g->sm - g->u0;
+    if (S > N - g->first) S = N - g->first;
+    if (S < 1) return 1;
+    g->S = S;
+    int M = 16;
+    while (M < S - 1) M <<= 1;
+    if (M > N) M = N;
+    g->zp.L = N; g->zp.M = M; g->zp.R = N / M;
+    g->out.W = pn; g->out.center = pn / 2;
+    g->zp.Wr = (pn + g->zp.R - 1) / g->zp.R;
+    if (dispatch_shape(M, &g->rows_fpc, &g->cols_cb)) return 1;
+    g->plane_elems = (size_t)g->sm * g->sm;
+    g->t_elems = (size_t)g->zp.R * S * g->zp.Wr;
+    return 0;
+}
+
+size_t litho_mask_spectrum_workspace_bytes(int pn, double eps, int N) {
+    SpecGeom g;
+    if (spec_geom(pn, eps, N, &g)) return 0;
+    return ((g.plane_elems * sizeof(float) + 15) / 16) * 16 + g.t_elems * sizeof(cplx);
+}
+
+int litho_mask_spectrum(const int16_t* geometry, int pn, double eps, int N, void* maskFT, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+    if (!geometry || !maskFT || !workspace) return fail(LITHO_ERR_ARG, "mask_spectrum: null argument");
+    SpecGeom g;
+    if (spec_geom(pn, eps, N, &g)) return fail(LITHO_ERR_ARG, "mask_spectrum: unsupported pn / eps / N");
+    if (workspace_bytes < litho_mask_spectrum_workspace_bytes(pn, eps, N))
+        return fail(LITHO_ERR_WORKSPACE, "mask_spectrum: workspace too small");
+    litho_stream_t st = (litho_stream_t)stream;
+    float* plane = (float*)workspace;
+    cplx* T = (cplx*)((char*)workspace + ((g.plane_elems * sizeof(float) + 15) / 16) * 16);
+    cplx* tw = nullptr;
+    BE_CHECK(get_twiddles(N, &tw));
+
+    ResampleParams rs;
+    rs.in = geometry; rs.pn = pn; rs.side = g.sm; rs.scale = (float)(1.0 / eps); rs.out = plane;
+#if defined(LITHO_EMU)
+    for (int y = 0; y < g.sm; ++y)
+        for (int x = 0; x < g.sm; ++x) resample_pixel(rs, y, x);
+#else
+    {
+        dim3 grid((g.sm + 255) / 256, g.sm, 1);
+        resample_kernel<<<grid, 256, 0, st>>>(rs);
+        BE_CHECK((int)cudaGetLastError());
+    }
+#endif
+    const int R = g.zp.R, M = g.zp.M;
+    AxisIn ax;
+    ax.first = g.first; ax.period = 1 << 30; ax.center = N / 2; ax.S = g.S;
+
+    RowsParams rp;
+    memset(&rp, 0, sizeof(rp));
+    rp.real_in = plane + (size_t)g.u0 * g.sm + g.u0;
+    rp.in_pitch = g.sm;
+    rp.lines = g.S;
+    rp.ax = ax; rp.out = g.out; rp.plan = g.zp; rp.twL = tw; rp.T = T;
+    ColsParams cp;
+    memset(&cp, 0, sizeof(cp));
+    cp.T = T; cp.batch = 1; cp.Rc = R; cp.Wrc = g.zp.Wr; cp.outc = g.out;
+    cp.ax = ax; cp.out = g.out; cp.plan = g.zp; cp.twL = tw;
+    cp.field = (cplx*)maskFT; cp.field_pitch = pn; cp.conj_out = 1; cp.scale = 1.f;
+    const int gx_rows = (g.S * R + g.rows_fpc - 1) / g.rows_fpc;
+    const int gx_cols = R * ((g.zp.Wr + g.cols_cb - 1) / g.cols_cb);
+    BE_CHECK(dispatch_rows(M, ROW_REAL_PLANE, rp, gx_rows, 1, st));
+    BE_CHECK(dispatch_cols(M, EPI_FIELD, cp, gx_cols, R, st));
+    return LITHO_OK;
+}
+
+// ---------------------------------------------------------------------------- direct solver
+static int direct_check(int pn, const int* bbox, int* Sr, int* Sc) {
+    if (pn < 2 || !bbox) return 1;
+    if (bbox[0] < 0 || bbox[2] < 0 || bbox[1] >= pn || bbox[3] >= pn || bbox[1] < bbox[0] || bbox[3] < bbox[2]) return 1;
+    *Sr = bbox[1] - bbox[0] + 1;
+    *Sc = bbox[3] - bbox[2] + 1;
+    return 0;
+}
+
+int litho_direct_operator(int pn, double pixelSize, double wavelength, int sign, void* A, void* stream) {
+    if (!A || pn < 2 || !(pixelSize > 0) || !(wavelength > 0) || (sign != 1 && sign != -1))
+        return fail(LITHO_ERR_ARG, "direct_operator: bad argument");
+    // python-double arithmetic of imageformation.py:4-8 / mask.py:32-35, then float32 like torch.arange
+    const double deltaK = 4.0 / (double)pn;
+    const double Kbound = (double)pn / 2.0 * deltaK;
+    const double pixelBound = (double)pn / 2.0 * pixelSize;
+    DirectOpParams P;
+    P.kstart = (float)(-Kbound); P.kstep = (float)deltaK;
+    P.xstart = (float)(-pixelBound); P.xstep = (float)pixelSize;
+    P.c0 = (float)(2.0 * M_PI / wavelength);
+    P.sign = sign; P.pn = pn; P.A = (cplx*)A;
+#if defined(LITHO_EMU)
+    (void)stream;
+    for (int a = 0; a < pn; ++a)
+        for (int c = 0; c < pn; ++c) direct_op_elem(P, a, c);
+#else
+    dim3 grid((pn + 255) / 256, pn, 1);
+    direct_op_kernel<<<grid, 256, 0, (litho_stream_t)stream>>>(P);
+    BE_CHECK((int)cudaGetLastError());
+#endif
+    return LITHO_OK;
+}
+
+size_t litho_direct_workspace_bytes(int pn, const int* bbox, int batch) {
+    int Sr, Sc;
+    if (direct_check(pn, bbox, &Sr, &Sc) || batch < 1) return 0;
+    return (size_t)batch * Sr * pn * sizeof(cplx);
+}
+
+static int direct_launch(int kind, int epi, const DirectParams& P, litho_stream_t st) {
+    const int gb = (P.pn + DT - 1) / DT, gu = (P.Sr + DT - 1) / DT;
+    const size_t smem = DIRECT_SMEM_ELEMS * sizeof(cplx);
+#if defined(LITHO_EMU)
+    (void)st;
+    if (kind == DIRECT_PUPIL_MASK)
+        litho_emu::launch(gb, gu, P.batch, DIRECT_THREADS, smem,
+                          [&](const litho_emu::EmuCtx& c, char* s) { direct_rows_body<DIRECT_PUPIL_MASK>(P, c, (cplx*)s); });
+    else
+        litho_emu::launch(gb, gu, P.batch, DIRECT_THREADS, smem,
+                          [&](const litho_emu::EmuCtx& c, char* s) { direct_rows_body<DIRECT_GEOMETRY>(P, c, (cplx*)s); });
+    if (epi == DIRECT_ACCUM)
+        litho_emu::launch(gb, gb, 1, DIRECT_THREADS, smem,
+                          [&](const litho_emu::EmuCtx& c, char* s) { direct_cols_body<DIRECT_ACCUM>(P, c, (cplx*)s); });
+    else
+        litho_emu::launch(gb, gb, 1, DIRECT_THREADS, smem,
+                          [&](const litho_emu::EmuCtx& c, char* s) { direct_cols_body<DIRECT_FIELD>(P, c, (cplx*)s); });
+    return 0;
+#else
+    dim3 g1(gb, gu, P.batch), g2(gb, gb, 1);
+    if (kind == DIRECT_PUPIL_MASK) direct_rows_kernel<DIRECT_PUPIL_MASK><<<g1, DIRECT_THREADS, smem, st>>>(P);
+    else direct_rows_kernel<DIRECT_GEOMETRY><<<g1, DIRECT_THREADS, smem, st>>>(P);
+    int e = (int)cudaGetLastError();
+    if (e) return e;
+    if (epi == DIRECT_ACCUM) direct_cols_kernel<DIRECT_ACCUM><<<g2, DIRECT_THREADS, smem, st>>>(P);
+    else direct_cols_kernel<DIRECT_FIELD><<<g2, DIRECT_THREADS, smem, st>>>(P);
+    return (int)cudaGetLastError();
+#endif
+}
+
+int litho_direct_accumulate(const void* A, const void* maskFT, const void* pupil, int pn, const int* bbox,
+                            const int32_t* shifts, const float* weights, int n_src, int batch, float* intensity,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+    int Sr, Sc;
+    if (!A || !maskFT || !pupil || !intensity || direct_check(pn, bbox, &Sr, &Sc))
+        return fail(LITHO_ERR_ARG, "direct_accumulate: bad argument");
+    if (n_src < 0) return fail(LITHO_ERR_ARG, "direct_accumulate: negative n_src");
+    if (n_src == 0) return LITHO_OK;
+    if (!shifts) return fail(LITHO_ERR_ARG, "direct_accumulate: shifts is null");
+    if (batch < 1) batch = 8;
+    if (batch > n_src) batch = n_src;
+    if (!workspace || workspace_bytes < litho_direct_workspace_bytes(pn, bbox, batch))
+        return fail(LITHO_ERR_WORKSPACE, "direct_accumulate: workspace too small");
+    DirectParams P;
+    memset(&P, 0, sizeof(P));
+    P.A = (const cplx*)A; P.pn = pn; P.pupil = (const cplx*)pupil; P.mask = (const cplx*)maskFT;
+    P.pr0 = bbox[0]; P.pc0 = bbox[2]; P.Sr = Sr; P.Sc = Sc;
+    P.shifts = (const int2_*)shifts; P.weights = weights;
+    P.T = (cplx*)workspace; P.intensity = intensity;
+    for (int s0 = 0; s0 < n_src; s0 += batch) {
+        P.s_begin = s0;
+        P.batch = (n_src - s0) < batch ? (n_src - s0) : batch;
+        BE_CHECK(direct_launch(DIRECT_PUPIL_MASK, DIRECT_ACCUM, P, (litho_stream_t)stream));
+    }
+    return LITHO_OK;
+}
+
+int litho_direct_field(const void* A, const void* pupil, const void* maskFT, int pn, const int* bbox, void* field,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+    int Sr, Sc;
+    if (!A || !maskFT || !pupil || !field || direct_check(pn, bbox, &Sr, &Sc))
+        return fail(LITHO_ERR_ARG, "direct_field: bad argument");
+    if (!workspace || workspace_bytes < litho_direct_workspace_bytes(pn, bbox, 1))
+        return fail(LITHO_ERR_WORKSPACE, "direct_field: workspace too small");
+    DirectParams P;
+    memset(&P, 0, sizeof(P));
+    P.A = (const cplx*)A; P.pn = pn; P.pupil = (const cplx*)pupil; P.mask = (const cplx*)maskFT;
+    P.pr0 = bbox[0]; P.pc0 = bbox[2]; P.Sr = Sr; P.Sc = Sc;
+    P.batch = 1; P.T = (cplx*)workspace; P.field = (cplx*)field;
+    BE_CHECK(direct_launch(DIRECT_PUPIL_MASK, DIRECT_FIELD, P, (litho_stream_t)stream));
+    return LITHO_OK;
+}
+
+int litho_direct_mask_spectrum(const void* Aplus, const int16_t* geometry, int pn, void* maskFT, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+    if (!Aplus || !geometry || !maskFT || pn < 2) return fail(LITHO_ERR_ARG, "direct_mask_spectrum: bad argument");
+    const int bbox[4] = {0, pn - 1, 0, pn - 1};
+    if (!workspace || workspace_bytes < litho_direct_workspace_bytes(pn, bbox, 1))
+        return fail(LITHO_ERR_WORKSPACE, "direct_mask_spectrum: workspace too small");
+    DirectParams P;
+    memset(&P, 0, sizeof(P));
+    P.A = (const cplx*)Aplus; P.pn = pn; P.geometry = geometry;
+    P.pr0 = 0; P.pc0 = 0; P.Sr = pn; P.Sc = pn;
+    P.batch = 1; P.T = (cplx*)workspace; P.field = (cplx*)maskFT;
+    BE_CHECK(direct_launch(DIRECT_GEOMETRY, DIRECT_FIELD, P, (litho_stream_t)stream));
     return LITHO_OK;
 }
 

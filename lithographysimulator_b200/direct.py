@@ -1,12 +1,98 @@
-"""Direct ("Abbe") solver -- reference imageformation.py:3-30 and mask.py:41-61."""
+"""Direct ("Abbe") solver -- reference imageformation.py:3-30 and mask.py:41-61.
+
+E = A * G * A^T with the fp16-quantised phase table, as two native complex matrix products per
+source point (csrc/direct_kernels.h).  CUDA only.
+"""
 from __future__ import annotations
 
-from ._native import LithoError
+import ctypes as C
+
+import torch
+
+from . import _native
+from .imaging import AbbeEngine, _as_c64, source_shifts
 
 
-def _missing(*_a, **_k):
-    raise LithoError("the direct (fft=False) solver kernels are not built into this library yet; "
-                     "there is no CPU fallback")
+def _operator(lib, pn: int, pixelSize, wavelength: float, sign: int, dev) -> torch.Tensor:
+    A = torch.empty((pn, pn), dtype=torch.complex64, device=dev)
+    lib.check(lib.litho_direct_operator(pn, float(pixelSize), float(wavelength), sign, A.data_ptr(),
+                                        torch.cuda.current_stream(dev).cuda_stream), "litho_direct_operator")
+    return A
 
 
-direct_field = direct_abbe_image = direct_mask_spectrum = _missing
+def _bbox_arg(bbox):
+    return (C.c_int * 4)(*bbox)
+
+
+def direct_abbe_image(maskFT, pupilF, lightsource, pixelSize, wavelength, dev, weights=None, batch: int = 8):
+    """abbeImage(fft=False): sum over source points of |A (roll(P) * M) A^T|^2, no post-processing
+    (reference imageformation.py:59-65, :77)."""
+    eng = AbbeEngine.get(dev)
+    lib = eng.lib
+    with torch.cuda.device(dev):
+        maskFT_d = _as_c64(maskFT, dev)
+        pupil_d = _as_c64(pupilF, dev)
+        pn = int(maskFT_d.shape[0])
+        shifts = source_shifts(lightsource.to(dev), pn)
+        n_src = int(shifts.shape[0])
+        out = torch.zeros((pn, pn), dtype=torch.float32, device=dev)
+        if n_src == 0:
+            return out
+        bbox = eng.pupil_bbox(pupil_d)
+        if bbox[1] < bbox[0]:
+            return out
+        A = _operator(lib, pn, pixelSize, wavelength, -1, dev)
+        batch = max(1, min(batch, n_src))
+        box = _bbox_arg(bbox)
+        nbytes = int(lib.litho_direct_workspace_bytes(pn, box, batch))
+        ws = eng.workspace(nbytes)
+        w_d = None if weights is None else weights.to(device=dev, dtype=torch.float32).contiguous()
+        lib.check(lib.litho_direct_accumulate(A.data_ptr(), maskFT_d.data_ptr(), pupil_d.data_ptr(), pn, box,
+                                              shifts.data_ptr(), None if w_d is None else w_d.data_ptr(), n_src, batch,
+                                              out.data_ptr(), ws.data_ptr(), nbytes, eng.stream()),
+                  "litho_direct_accumulate")
+        return out
+
+
+def direct_field(pupil, maskFT, fraunhoferConstant, pixelNumber, pixelSize, dev) -> torch.Tensor:
+    """calculateAerial: complex field of one (already shifted) pupil.  The wavelength is recovered from
+    the reference's `fraunhoferConstant` = -2*pi*i/lambda argument (imageformation.py:52)."""
+    eng = AbbeEngine.get(dev)
+    lib = eng.lib
+    const = complex(fraunhoferConstant)
+    if const.imag == 0:
+        raise _native.LithoError("calculateAerial: fraunhoferConstant must be +-2*pi*i/wavelength")
+    sign = -1 if const.imag < 0 else 1
+    wavelength = 2 * torch.pi / abs(const.imag)
+    with torch.cuda.device(dev):
+        maskFT_d = _as_c64(maskFT, dev)
+        pupil_d = _as_c64(pupil, dev)
+        pn = int(maskFT_d.shape[0])
+        field = torch.zeros((pn, pn), dtype=torch.complex64, device=dev)
+        bbox = eng.pupil_bbox(pupil_d)
+        if bbox[1] < bbox[0]:
+            return field
+        A = _operator(lib, pn, pixelSize, wavelength, sign, dev)
+        box = _bbox_arg(bbox)
+        nbytes = int(lib.litho_direct_workspace_bytes(pn, box, 1))
+        ws = eng.workspace(nbytes)
+        lib.check(lib.litho_direct_field(A.data_ptr(), pupil_d.data_ptr(), maskFT_d.data_ptr(), pn, box,
+                                         field.data_ptr(), ws.data_ptr(), nbytes, eng.stream()), "litho_direct_field")
+        return field
+
+
+def direct_mask_spectrum(geometry, pixelSize, wavelength, dev) -> torch.Tensor:
+    """Mask.fraunhofer(fft=False): A+ * geometry * A+^T (reference mask.py:41-61)."""
+    eng = AbbeEngine.get(dev)
+    lib = eng.lib
+    with torch.cuda.device(dev):
+        geom = geometry.to(device=dev, dtype=torch.int16).contiguous()
+        pn = int(geom.shape[0])
+        A = _operator(lib, pn, pixelSize, wavelength, +1, dev)
+        box = _bbox_arg((0, pn - 1, 0, pn - 1))
+        nbytes = int(lib.litho_direct_workspace_bytes(pn, box, 1))
+        ws = eng.workspace(nbytes)
+        out = torch.empty((pn, pn), dtype=torch.complex64, device=dev)
+        lib.check(lib.litho_direct_mask_spectrum(A.data_ptr(), geom.data_ptr(), pn, out.data_ptr(), ws.data_ptr(),
+                                                 nbytes, eng.stream()), "litho_direct_mask_spectrum")
+        return out

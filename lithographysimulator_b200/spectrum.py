@@ -3,20 +3,24 @@ from __future__ import annotations
 
 import torch
 
+from . import _native
+
 
 def mask_spectrum_fft(geometry: torch.Tensor, epsilon: float, N: int, device: torch.device) -> torch.Tensor:
     """Bilinear upsample by epsilon, centre-pad to N, centred forward DFT, crop to pn x pn (complex64).
 
-    Run-once per mask.  Staging through torch device ops (resample / pad / cuFFT) until the native
-    zoom-DFT entry point for real input planes is wired in (kernels exist: ROW_REAL_PLANE).
+    One native call (litho_mask_spectrum): a resample kernel followed by the same pruned zoom-DFT
+    row/column kernels the imaging path uses, with a conjugating epilogue for the forward sign.
     """
-    pn = int(geometry.shape[0])
-    g = geometry.to(device=device, dtype=torch.float32)[None, None]
-    scaled = torch.nn.functional.interpolate(g, scale_factor=epsilon, mode="bilinear")[0, 0]
-    sm = int(scaled.shape[0])
-    lead = ((N - pn) - (sm - pn)) // 2
-    trail = lead + sm % 2
-    padded = torch.nn.functional.pad(scaled, (lead, trail, lead, trail))
-    spec = torch.fft.ifftshift(torch.fft.fft2(torch.fft.fftshift(padded), norm="backward"))
-    trim = (N - pn) // 2
-    return spec[trim:spec.shape[0] - trim, trim:spec.shape[1] - trim].contiguous()
+    lib = _native.device_lib()
+    with torch.cuda.device(device):
+        geom = geometry.to(device=device, dtype=torch.int16).contiguous()
+        pn = int(geom.shape[0])
+        nbytes = int(lib.litho_mask_spectrum_workspace_bytes(pn, float(epsilon), int(N)))
+        if nbytes == 0:
+            raise _native.LithoError(f"mask spectrum: unsupported configuration pn={pn}, eps={epsilon}, N={N}")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        out = torch.empty((pn, pn), dtype=torch.complex64, device=device)
+        lib.check(lib.litho_mask_spectrum(geom.data_ptr(), pn, float(epsilon), int(N), out.data_ptr(), ws.data_ptr(),
+                                          nbytes, torch.cuda.current_stream(device).cuda_stream), "litho_mask_spectrum")
+        return out

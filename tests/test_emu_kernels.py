@@ -65,6 +65,78 @@ def test_emu_larger_subfft_sizes():
         assert O.rel_l2(img, np.abs(e) ** 2) < H.TOL, info
 
 
+@pytest.mark.parametrize("name", ["demo64_quasar", "ps50_64", "ps12_64", "np2_96", "wrap_128"])
+def test_emu_mask_spectrum_matches_reference(name):
+    """Mask._ffFraunhofer through litho_mask_spectrum (incl. N == pn, where the resampled mask is cropped)."""
+    c = KAT[name]
+    lib = H.emu_lib()
+    geom = np.ascontiguousarray(c["geometry"], dtype=np.int16)
+    pn = geom.shape[0]
+    eps, N = float(c["eps"]), int(c["N"])
+    nbytes = lib.litho_mask_spectrum_workspace_bytes(pn, eps, N)
+    assert nbytes > 0
+    ws = np.zeros(nbytes, np.uint8)
+    out = np.zeros((pn, pn), np.complex64)
+    lib.check(lib.litho_mask_spectrum(geom.ctypes.data, pn, eps, N, out.ctypes.data, ws.ctypes.data, nbytes, None))
+    assert np.linalg.norm(out - c["maskFT"]) / np.linalg.norm(c["maskFT"]) < H.TOL
+
+
+def _emu_direct_operator(lib, pn, ps, sign):
+    A = np.zeros((pn, pn), np.complex64)
+    lib.check(lib.litho_direct_operator(pn, float(ps), 193.0, sign, A.ctypes.data, None))
+    return A
+
+
+@pytest.mark.parametrize("name", ["direct_64", "direct_128"])
+def test_emu_direct_solver_matches_reference(name):
+    """abbeImage(fft=False) and Mask.fraunhofer(fft=False) through the direct-solver kernels."""
+    import ctypes as C
+    c = KAT[name]
+    lib = H.emu_lib()
+    pn = c["maskFT"].shape[0]
+    ps = int(c["pixel_size"])
+    A = _emu_direct_operator(lib, pn, ps, -1)
+    assert np.abs(A - O.direct_operator(pn, ps, 193.0, -1.0, np.complex128)).max() < 2e-6
+    mft = np.ascontiguousarray(c["maskFT"])
+    pup = np.ascontiguousarray(c["pupil"])
+    bbox = lib.pupil_bbox(pup.ctypes.data, pn)
+    box = (C.c_int * 4)(*bbox)
+    shifts = np.ascontiguousarray(O.source_shifts(c["lightsource"], pn))
+    n = len(shifts)
+    nbytes = lib.litho_direct_workspace_bytes(pn, box, 2)
+    ws = np.zeros(nbytes, np.uint8)
+    img = np.zeros((pn, pn), np.float32)
+    lib.check(lib.litho_direct_accumulate(A.ctypes.data, mft.ctypes.data, pup.ctypes.data, pn, box, shifts.ctypes.data,
+                                          None, n, 2, img.ctypes.data, ws.ctypes.data, nbytes, None))
+    assert O.rel_l2(img, c["image"]) < H.TOL
+    # mask spectrum by the direct integral
+    Ap = _emu_direct_operator(lib, pn, ps, +1)
+    geom = np.ascontiguousarray(c["geometry"], dtype=np.int16)
+    full = (C.c_int * 4)(0, pn - 1, 0, pn - 1)
+    nbytes = lib.litho_direct_workspace_bytes(pn, full, 1)
+    ws = np.zeros(nbytes, np.uint8)
+    out = np.zeros((pn, pn), np.complex64)
+    lib.check(lib.litho_direct_mask_spectrum(Ap.ctypes.data, geom.ctypes.data, pn, out.ctypes.data, ws.ctypes.data,
+                                             nbytes, None))
+    assert np.linalg.norm(out - c["maskFT"]) / np.linalg.norm(c["maskFT"]) < H.TOL
+
+
+def test_emu_direct_field():
+    import ctypes as C
+    d = KAT["field_direct_64"]
+    lib = H.emu_lib()
+    A = _emu_direct_operator(lib, 64, 25, -1)
+    pf = np.ascontiguousarray(d["pf"])
+    mft = np.ascontiguousarray(d["maskFT"])
+    box = (C.c_int * 4)(*lib.pupil_bbox(pf.ctypes.data, 64))
+    nbytes = lib.litho_direct_workspace_bytes(64, box, 1)
+    ws = np.zeros(nbytes, np.uint8)
+    field = np.zeros((64, 64), np.complex64)
+    lib.check(lib.litho_direct_field(A.ctypes.data, pf.ctypes.data, mft.ctypes.data, 64, box, field.ctypes.data,
+                                     ws.ctypes.data, nbytes, None))
+    assert np.linalg.norm(field - d["field"]) / np.linalg.norm(d["field"]) < H.TOL
+
+
 def test_emu_rejects_unsupported():
     lib = H.emu_lib()
     with pytest.raises(Exception):
