@@ -14,6 +14,9 @@
 //                      batch in registers and added to the intensity (or E stored as a field).
 #pragma once
 #include "hd.h"
+#if defined(__CUDACC__)
+#include <cuda_fp16.h>
+#endif
 
 namespace litho {
 
