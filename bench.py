@@ -198,7 +198,9 @@ def run_ours(args):
     shifts_all = source_shifts(ls_d, pn)
     n_src = int(shifts_all.shape[0])
     shifts_mine = shifts_all[rank::world].contiguous()  # interleaved shard: equal work per rank
-    plan = eng.plan(pn, N, eng.pupil_bbox(pf_d))
+    support = eng.pupil_support(pf_d)
+    # one plan for all ranks, chosen from ALL source points (the partial planes are summed)
+    plan = eng.plan(pn, N, support, generic=True) if args.generic else eng.plan_for(pn, N, support, shifts_all)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def reduce_fn(inten):
@@ -287,7 +289,7 @@ def run_ours(args):
     mask_obj = None
 
     def e2e_once():
-        img_d = eng.abbe_fft(mft_p, pf_p, ls_p, cfg.pixel_size, 4 / pn, cfg.wavelength, reduce_fn=reduce_fn,
+        img_d = eng.abbe_fft(mft_p, pf_p, ls_p, cfg.pixel_size, 4 / pn, cfg.wavelength, reduce_fn=reduce_fn, plan=plan,
                              batch=args.batch)
         out_p.copy_(img_d, non_blocking=True)
         torch.cuda.synchronize(dev)
@@ -321,7 +323,8 @@ def run_ours(args):
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         step_ach = algorithmic_flops(pn, N, n_src)["total"] / (ms_per_step * 1e-3) / 1e12
         roofline = {
-            "bound": "fp32", "kernel": "abbe_cols_kernel (column pass + |E|^2 accumulate)",
+            "bound": "fp32", "kernel": ("abbe_fast_cols_kernel" if plan.path == 2 else "abbe_cols_kernel") +
+                      " (column pass + |E|^2 accumulate)",
             "achieved": achieved, "peak": best, "unit": "TFLOP/s", "frac": achieved / best if best else None,
             "peak_source": "FP32 FMA probe measured in this run (MEASURED_PEAKS.json has no FP32 entry); "
                            f"nominal {peak_nominal:.1f} TFLOP/s = SMs*128*2*max clock",
@@ -334,7 +337,8 @@ def run_ours(args):
             "hbm": {"compulsory_bytes_per_image": 8 * pn * pn * 2 + 8 * n_src + 4 * pn * pn,
                     "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
         }
-        launches_per_step = 2 * ((n_mine + batch - 1) // batch) + 1
+        # rows + cols per batch, plus per image: rim sums and the 6 interpolation kernels (fast path) + resample
+        launches_per_step = 2 * ((n_mine + batch - 1) // batch) + (8 if plan.path == 2 else 1)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
@@ -349,7 +353,9 @@ def run_ours(args):
                 "config": {"workload": f"{cfg.name}: {pn}^2 {cfg.mask} mask, {cfg.source} source {n_src} pts, N={N}, "
                                        "Zernike-aberrated pupil, FFT-approximation solver",
                            "l2": "flushed (256 MB write) between timed iterations", "batch": batch,
-                           "subfft": plan.M, "residues": plan.R, "sharding": f"source points interleaved over {world} rank(s), "
+                           "subfft": plan.M, "residues": plan.R,
+                           "path": "fast coarse-grid (2 FFTs of length M per line, spectral interpolation once per image)"
+                           if plan.path == 2 else "generic fine-grid", "sharding": f"source points interleaved over {world} rank(s), "
                                                                            "one NCCL all-reduce of the intensity plane"},
                 "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
                 "e2e": {"value": 1.0 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -369,6 +375,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--ref-sample", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--generic", action="store_true", help="force the generic fine-grid kernels")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -38,10 +38,15 @@ typedef struct litho_plan_info {
     int pn, N;            /* grid side, FFT-approximation length (mask.py:67-72) */
     int bbox[4];          /* pupil support r0,r1,c0,c1 (inclusive) */
     int L, M, R, Wr;      /* transform length, sub-FFT length, residues, per-residue pitch */
-    int path;             /* 1 = fine grid (exact for any source) */
+    int path;             /* 1 = generic fine-grid kernels (any source, any pupil);
+                             2 = fast coarse-grid kernels (need every shift inside shift_range) */
     int default_batch;    /* source points per launch pair used when batch <= 0 */
-    uint64_t intensity_elems; /* float elements of the residue-major intensity plane */
+    uint64_t intensity_elems; /* float elements of the plan's intensity accumulator */
+    int shift_range[4];   /* d0 min,max, d1 min,max for which roll() does not wrap the pupil window */
 } litho_plan_info_t;
+
+/* litho_plan_create flags */
+#define LITHO_PLAN_GENERIC 1  /* force path 1 (required when a source point wraps the pupil window) */
 
 int litho_abi_version(void);
 const char* litho_last_error(void);
@@ -56,9 +61,21 @@ int litho_epsilon_n(double deltaK, double pixelSize, double wavelength, double* 
  * moves around the grid).  Synchronises `stream`; bbox_host = {r0,r1,c0,c1}, {0,-1,0,-1} if empty. */
 int litho_pupil_bbox(const void* pupil, int pn, int* bbox_host, void* stream);
 
+/* Support analysis used to plan the fast path: support_host[0..3] = bbox as above, [4..11] = non-zero
+ * extents {cmin,cmax} of the first and last bbox row and {rmin,rmax} of the first and last bbox column
+ * (the pupil's rim pixels, which carry the one frequency line the coarse grid aliases).  Synchronises. */
+int litho_pupil_support(const void* pupil, int pn, int* support_host, void* stream);
+
+/* min/max of the source shifts: bounds_host = {d0 min, d0 max, d1 min, d1 max}.  Synchronises.
+ * A fast plan (path 2) may only be used when these lie inside plan_info.shift_range. */
+int litho_shift_bounds(const int32_t* shifts, int n_src, int* bounds_host, void* stream);
+
 /* Plan for abbeImage(fft=True) on a pn x pn grid with FFT-approximation length N.
- * flags: reserved, pass 0. */
+ * litho_plan_create takes the 4-int bbox; litho_plan_create_ex the 12-int support of
+ * litho_pupil_support (cheaper rim sums).  flags: 0 or LITHO_PLAN_GENERIC.
+ * Path 2 is chosen when the window fits S <= M+1, M a power of two <= 4096, and 2M <= N. */
 int litho_plan_create(int pn, int N, const int* bbox, int flags, litho_plan_t** plan);
+int litho_plan_create_ex(int pn, int N, const int* support, int flags, litho_plan_t** plan);
 void litho_plan_destroy(litho_plan_t* plan);
 int litho_plan_get_info(const litho_plan_t* plan, litho_plan_info_t* info);
 size_t litho_plan_workspace_bytes(const litho_plan_t* plan, int batch);
@@ -84,10 +101,13 @@ int litho_abbe_fft_accumulate_ex(const litho_plan_t* plan, const void* maskFT, c
 /* Post-processing of abbeImage(fft=True)                      imageformation.py:69-75
  * abs -> bilinear resample by 1/eps -> zero border; out has litho_fft_output_side(pn,eps)^2 floats. */
 int litho_fft_output_side(int pn, double eps);
+/* workspace for finalize / unpermute: staging of the coarse->fine spectral interpolation (path 2) */
+size_t litho_plan_finalize_workspace_bytes(const litho_plan_t* plan);
 int litho_abbe_fft_finalize(const litho_plan_t* plan, const float* intensity, double eps, float* out,
-                            void* stream);
+                            void* workspace, size_t workspace_bytes, void* stream);
 /* Raw accumulated intensity in natural row-major order (pn x pn), no resampling. */
-int litho_abbe_fft_unpermute(const litho_plan_t* plan, const float* intensity, float* out, void* stream);
+int litho_abbe_fft_unpermute(const litho_plan_t* plan, const float* intensity, float* out, void* workspace,
+                             size_t workspace_bytes, void* stream);
 
 /* calculateFFTAerial(pf, maskFFFT, pixelNumber, N)              imageformation.py:32-45
  * complex field (pn x pn complex64) of one already-shifted pupil `pf`; the plan must have been

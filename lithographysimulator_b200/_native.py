@@ -22,7 +22,9 @@ class LithoError(RuntimeError):
 class PlanInfo(C.Structure):
     _fields_ = [("pn", C.c_int), ("N", C.c_int), ("bbox", C.c_int * 4), ("L", C.c_int), ("M", C.c_int),
                 ("R", C.c_int), ("Wr", C.c_int), ("path", C.c_int), ("default_batch", C.c_int),
-                ("intensity_elems", C.c_uint64)]
+                ("intensity_elems", C.c_uint64), ("shift_range", C.c_int * 4)]
+
+PLAN_GENERIC = 1
 
 
 # every symbol include/litho_b200.h declares: (name, restype, argtypes)
@@ -33,7 +35,11 @@ SYMBOLS = [
     ("litho_is_device_build", C.c_int, []),
     ("litho_epsilon_n", C.c_int, [C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     ("litho_pupil_bbox", C.c_int, [_P, C.c_int, C.POINTER(C.c_int), _P]),
+    ("litho_pupil_support", C.c_int, [_P, C.c_int, C.POINTER(C.c_int), _P]),
+    ("litho_shift_bounds", C.c_int, [_P, C.c_int, C.POINTER(C.c_int), _P]),
     ("litho_plan_create", C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(_P)]),
+    ("litho_plan_create_ex", C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(_P)]),
+    ("litho_plan_finalize_workspace_bytes", C.c_size_t, [_P]),
     ("litho_plan_destroy", None, [_P]),
     ("litho_plan_get_info", C.c_int, [_P, C.POINTER(PlanInfo)]),
     ("litho_plan_workspace_bytes", C.c_size_t, [_P, C.c_int]),
@@ -49,8 +55,8 @@ SYMBOLS = [
     ("litho_direct_mask_spectrum", C.c_int, [_P, _P, C.c_int, _P, _P, C.c_size_t, _P]),
     ("litho_fp32_probe", C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_double), _P]),
     ("litho_fft_output_side", C.c_int, [C.c_int, C.c_double]),
-    ("litho_abbe_fft_finalize", C.c_int, [_P, _P, C.c_double, _P, _P]),
-    ("litho_abbe_fft_unpermute", C.c_int, [_P, _P, _P, _P]),
+    ("litho_abbe_fft_finalize", C.c_int, [_P, _P, C.c_double, _P, _P, C.c_size_t, _P]),
+    ("litho_abbe_fft_unpermute", C.c_int, [_P, _P, _P, _P, C.c_size_t, _P]),
     ("litho_fft_field", C.c_int, [_P, _P, _P, _P, _P, C.c_size_t, _P]),
 ]
 
@@ -90,10 +96,25 @@ class NativeLib:
         self.check(self.litho_pupil_bbox(pupil_ptr, pn, box, stream), "litho_pupil_bbox")
         return tuple(box)
 
-    def plan_create(self, pn: int, N: int, bbox, flags: int = 0) -> "Plan":
-        box = (C.c_int * 4)(*bbox)
+    def pupil_support(self, pupil_ptr: int, pn: int, stream: int = 0):
+        sup = (C.c_int * 12)()
+        self.check(self.litho_pupil_support(pupil_ptr, pn, sup, stream), "litho_pupil_support")
+        return tuple(sup)
+
+    def shift_bounds(self, shifts_ptr, n_src: int, stream: int = 0):
+        b = (C.c_int * 4)()
+        self.check(self.litho_shift_bounds(shifts_ptr, n_src, b, stream), "litho_shift_bounds")
+        return tuple(b)
+
+    def plan_create(self, pn: int, N: int, support, flags: int = 0) -> "Plan":
+        """`support` is the 4-int bbox or the 12-int result of pupil_support()."""
         handle = _P()
-        self.check(self.litho_plan_create(pn, N, box, flags, C.byref(handle)), "litho_plan_create")
+        if len(support) == 12:
+            arr = (C.c_int * 12)(*support)
+            self.check(self.litho_plan_create_ex(pn, N, arr, flags, C.byref(handle)), "litho_plan_create_ex")
+        else:
+            arr = (C.c_int * 4)(*support)
+            self.check(self.litho_plan_create(pn, N, arr, flags, C.byref(handle)), "litho_plan_create")
         return Plan(self, handle)
 
 
@@ -108,6 +129,8 @@ class Plan:
         self.bbox = tuple(info.bbox)
         self.intensity_elems = int(info.intensity_elems)
         self.default_batch = info.default_batch
+        self.path = info.path
+        self.shift_range = tuple(info.shift_range)
 
     def workspace_bytes(self, batch: int = 0) -> int:
         return int(self.lib.litho_plan_workspace_bytes(self.handle, batch))
@@ -121,13 +144,21 @@ class Plan:
     def output_side(self, eps: float) -> int:
         return int(self.lib.litho_fft_output_side(self.pn, eps))
 
-    def finalize(self, intensity, eps, out, stream=0):
-        self.lib.check(self.lib.litho_abbe_fft_finalize(self.handle, intensity, eps, out, stream),
-                       "litho_abbe_fft_finalize")
+    def shifts_fit(self, bounds) -> bool:
+        """True if shift bounds {d0 min,max,d1 min,max} keep roll() from wrapping the pupil window."""
+        r = self.shift_range
+        return bounds[0] >= r[0] and bounds[1] <= r[1] and bounds[2] >= r[2] and bounds[3] <= r[3]
 
-    def unpermute(self, intensity, out, stream=0):
-        self.lib.check(self.lib.litho_abbe_fft_unpermute(self.handle, intensity, out, stream),
-                       "litho_abbe_fft_unpermute")
+    def finalize_workspace_bytes(self) -> int:
+        return int(self.lib.litho_plan_finalize_workspace_bytes(self.handle))
+
+    def finalize(self, intensity, eps, out, workspace=None, workspace_bytes=0, stream=0):
+        self.lib.check(self.lib.litho_abbe_fft_finalize(self.handle, intensity, eps, out, workspace, workspace_bytes,
+                                                        stream), "litho_abbe_fft_finalize")
+
+    def unpermute(self, intensity, out, workspace=None, workspace_bytes=0, stream=0):
+        self.lib.check(self.lib.litho_abbe_fft_unpermute(self.handle, intensity, out, workspace, workspace_bytes,
+                                                         stream), "litho_abbe_fft_unpermute")
 
     def fft_field(self, pf, maskFT, field, workspace, workspace_bytes, stream=0):
         self.lib.check(self.lib.litho_fft_field(self.handle, pf, maskFT, field, workspace, workspace_bytes, stream),

@@ -57,6 +57,7 @@ struct ColsParams {
     float* iperm;
     // EPI_FIELD: field[o_r*field_pitch + o_c] = E (conjugated if conj_out)
     cplx* field;
+    float* real_out;  // when non-null only the real part is stored here (same pitch)
     int field_pitch;
     int conj_out;
     float scale;
@@ -131,7 +132,7 @@ LITHO_HD void rows_body(const RowsParams& P, const Ctx& ctx, cplx* smem) {
         for (int e = 0; e < 16; ++e) v[e] = mk(0.f, 0.f);
     }
 
-    fft_run<M, false>(v, smem + grp * Sh::SMEM_ELEMS, 1, g, P.twL, R, ctx);
+    fft_run<M, 16, false>(v, smem + grp * Sh::SMEM_ELEMS, 1, g, GlobalTw<M, 16>{P.twL, R}, CtaSync<Ctx>{ctx});
 
     if (active) {
         const int kmin = zoom_kmin(P.out, R, r);
@@ -182,7 +183,7 @@ LITHO_HD void cols_body(const ColsParams& P, const Ctx& ctx, cplx* smem) {
             for (int e = 0; e < 16; ++e) v[e] = mk(0.f, 0.f);
         }
 
-        fft_run<M, false>(v, smem + col, CB, g, P.twL, R, ctx);
+        fft_run<M, 16, false>(v, smem + col, CB, g, GlobalTw<M, 16>{P.twL, R}, CtaSync<Ctx>{ctx});
 
         if constexpr (EPI == EPI_ACCUM) {
             const float w = P.weights ? P.weights[P.s_begin + sl] : 1.f;
@@ -211,7 +212,8 @@ LITHO_HD void cols_body(const ColsParams& P, const Ctx& ctx, cplx* smem) {
                 cplx o = v[e];
                 o.x *= P.scale;
                 o.y *= P.conj_out ? -P.scale : P.scale;
-                P.field[(size_t)orow * P.field_pitch + oc] = o;
+                if (P.real_out) P.real_out[(size_t)orow * P.field_pitch + oc] = o.x;
+                else P.field[(size_t)orow * P.field_pitch + oc] = o;
             }
         }
     }
@@ -220,10 +222,19 @@ LITHO_HD void cols_body(const ColsParams& P, const Ctx& ctx, cplx* smem) {
 // ----------------------------------------------------------------------------- finalize
 // Natural-order read of the residue-major intensity plane.
 struct PermView {
+    int mode;  // 0: residue-major plane of the generic path, 1: natural row-major plane,
+               // 2: coarse plane of the fast path [2][2][M][M] when Nc == N (no interpolation needed)
     const float* iperm;
     AxisOut outr, outc;  // row / column output axes (W = pn, center = pn//2)
     int Rr, Rc, Wrr, Wrc;
+    int pitch;           // mode 1
+    int Mc, center;      // mode 2: sub-FFT length and pn//2; fine index i' = i - center, o = i' mod 2M
     LITHO_HD float at(int i, int j) const {
+        if (mode == 1) return iperm[(size_t)i * pitch + j];
+        if (mode == 2) {
+            const int oi = (i - center) & (2 * Mc - 1), oj = (j - center) & (2 * Mc - 1);
+            return iperm[((size_t)((oi & 1) * 2 + (oj & 1)) * Mc + (oi >> 1)) * Mc + (oj >> 1)];
+        }
         int rr, kr, rc, kc;
         zoom_split(outr, Rr, i, rr, kr);
         zoom_split(outc, Rc, j, rc, kc);

@@ -82,10 +82,49 @@ LITHO_HD void dft16(cplx (&a)[16]) {
     }
 }
 
+template <bool FWD>
+LITHO_HD void dft32(cplx (&a)[32]) {
+    // cos/sin(k*pi/16), k = 0..15
+    const float C[16] = {1.0f, 0.98078528040323044913f, 0.92387953251128675613f, 0.83146961230254523708f,
+                         0.70710678118654752440f, 0.55557023301960222474f, 0.38268343236508977173f,
+                         0.19509032201612826785f, 0.0f, -0.19509032201612826785f, -0.38268343236508977173f,
+                         -0.55557023301960222474f, -0.70710678118654752440f, -0.83146961230254523708f,
+                         -0.92387953251128675613f, -0.98078528040323044913f};
+    const float S[16] = {0.0f, 0.19509032201612826785f, 0.38268343236508977173f, 0.55557023301960222474f,
+                         0.70710678118654752440f, 0.83146961230254523708f, 0.92387953251128675613f,
+                         0.98078528040323044913f, 1.0f, 0.98078528040323044913f, 0.92387953251128675613f,
+                         0.83146961230254523708f, 0.70710678118654752440f, 0.55557023301960222474f,
+                         0.38268343236508977173f, 0.19509032201612826785f};
+    cplx e[16], o[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        e[i] = a[2 * i];
+        o[i] = a[2 * i + 1];
+    }
+    dft16<FWD>(e);
+    dft16<FWD>(o);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        cplx t;
+        if (k == 0) t = o[0];
+        else if (k == 8) t = mul_i<FWD>(o[8]);
+        else t = mul_w<FWD>(o[k], C[k], S[k]);
+        a[k] = cadd(e[k], t);
+        a[k + 16] = csub(e[k], t);
+    }
+}
+
 // Generic entry: radix-R DFT over the register subset v[B + t*STRIDE], t = 0..R-1.
 template <int R, int STRIDE, int B, bool FWD, int NV>
 LITHO_HD void dft_strided(cplx (&v)[NV]) {
-    if constexpr (R == 2) {
+    if constexpr (R == 32) {
+        cplx a[32];
+#pragma unroll
+        for (int t = 0; t < 32; ++t) a[t] = v[B + t * STRIDE];
+        dft32<FWD>(a);
+#pragma unroll
+        for (int t = 0; t < 32; ++t) v[B + t * STRIDE] = a[t];
+    } else if constexpr (R == 2) {
         dft2<FWD>(v[B], v[B + STRIDE]);
     } else if constexpr (R == 4) {
         dft4<FWD>(v[B], v[B + STRIDE], v[B + 2 * STRIDE], v[B + 3 * STRIDE]);
@@ -97,7 +136,7 @@ LITHO_HD void dft_strided(cplx (&v)[NV]) {
 #pragma unroll
         for (int t = 0; t < 8; ++t) v[B + t * STRIDE] = a[t];
     } else {
-        static_assert(R == 16, "radix must be 2, 4, 8 or 16");
+        static_assert(R == 16, "radix must be 2, 4, 8, 16 or 32");
         cplx a[16];
 #pragma unroll
         for (int t = 0; t < 16; ++t) a[t] = v[B + t * STRIDE];

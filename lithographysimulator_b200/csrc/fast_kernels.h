@@ -1,0 +1,318 @@
+// Fast path of the Abbe FFT-approximation hot loop (reference imageformation.py:59-67).
+//
+// Preconditions (checked on the host, litho_abi.cu): no source point makes roll() wrap the pupil
+// window around the grid, and the window fits S <= M+1 with M a power of two (M = pn/2 for the
+// reference's pupils).  Then two facts make the loop ~4x cheaper than the literal algorithm:
+//
+//  1. Shift equivalence.  The window's position only multiplies the field by
+//     unit-modulus phase ramps, which |E|^2 removes, so the inputs are indexed 0..S-1 for every
+//     source point and all twiddles become per-thread constants held in shared-memory tables.
+//
+//  2. Coarse sampling.  |E_s|^2 is a trigonometric polynomial with frequencies |d| <= S-1 <= M
+//     (in units of 1/N), so its samples on the Nc = 2M grid of spacing q = N/Nc determine it.
+//     Each 1-D transform is then an Nc-point DFT of <= M+1 inputs = 2 length-M FFTs
+//         X[2k+r] = FFT_M( x[u] * w_Nc^(r*u) folded modulo M )[k],   r = 0,1
+//     with every output used, instead of R = N/M pruned ones.  The intensity is accumulated on the
+//     coarse grid and interpolated exactly (spectrally) to the reference's pn centre pixels once
+//     per image (litho_abi.cu: finalize).  The single aliased frequency line |d| = M, which exists
+//     only when S = M+1 (the pupil's fp16 rim pixels), is carried separately by rim_body below.
+//
+// FFTs use 32 points per thread (radix 32 x 32 for M = 1024): one shared-memory exchange per FFT.
+#pragma once
+#include "fft_core.h"
+
+namespace litho {
+
+LITHO_HD int iclamp(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+template <int M>
+struct FastShape {
+    using Sh = FftShape<M, 32>;
+    static constexpr int TG = Sh::TG;
+    static constexpr int R1 = Sh::NP > 1 ? Sh::radix(1) : 1;
+    static constexpr int R2 = Sh::NP > 2 ? Sh::radix(2) : 1;
+    static constexpr int NS1 = 32, NS2 = 32 * R1;
+    // shared-memory twiddle tables: pre[u] = w_2M^u (u = 0..M), tw1[(t-1)*NS1+k], tw2[(t-1)*NS2+k]
+    static constexpr int PRE_OFF = 0;
+    static constexpr int TW1_OFF = M + 1;
+    static constexpr int TW2_OFF = TW1_OFF + (R1 - 1) * NS1;
+    static constexpr int NTAB = TW2_OFF + (R2 - 1) * NS2;
+    static constexpr int NTAB_PAD = (NTAB + 1) & ~1;  // keep the exchange region 16-byte aligned
+    // rows kernel: one FFT group per TG threads
+    static constexpr bool WARP_GROUP = (TG <= 32);
+    static constexpr int ROW_THREADS = WARP_GROUP ? 256 : TG;
+    static constexpr int ROW_GROUPS = ROW_THREADS / TG;
+    static constexpr size_t ROW_SMEM = (size_t)(NTAB_PAD + ROW_GROUPS * Sh::SMEM_ELEMS) * sizeof(cplx);
+    // cols kernel: CB adjacent columns per CTA, column fastest in the thread index
+    static constexpr int CB = (M <= 512) ? 16 : (M == 1024 ? 8 : 4);
+    static constexpr int COL_THREADS = CB * TG;
+    static constexpr size_t COL_SMEM = (size_t)(NTAB_PAD + CB * Sh::SMEM_ELEMS) * sizeof(cplx);
+    // occupancy targets: 128 registers per thread, i.e. 512 resident threads per SM
+    static constexpr int COL_MIN_BLOCKS = (512 / COL_THREADS) >= 1 ? (512 / COL_THREADS) : 1;
+    static constexpr int ROW_MIN_BLOCKS = (512 / ROW_THREADS) >= 1 ? (512 / ROW_THREADS) : 1;
+};
+
+template <int M>
+struct SmemTw {
+    const cplx* tab;
+    template <int PASS>
+    LITHO_HD cplx get(int t, int k) const {
+        using F = FastShape<M>;
+        if constexpr (PASS == 1) return tab[F::TW1_OFF + (t - 1) * F::NS1 + k];
+        else return tab[F::TW2_OFF + (t - 1) * F::NS2 + k];
+    }
+};
+
+template <class Ctx, bool WARP>
+struct GroupSync {
+    const Ctx& ctx;
+    LITHO_HD void sync() const {
+        if constexpr (WARP) ctx.sync_warp();
+        else ctx.sync();
+    }
+};
+
+struct FastRowsParams {
+    const cplx* pupil;
+    const cplx* mask;
+    int pn;
+    int pr0, pc0, Sr, Sc;
+    const int2_* shifts;
+    int s_begin, batch;
+    const cplx* tables;
+    cplx* T;  // [batch][2][Sr][M]
+};
+
+struct FastColsParams {
+    const cplx* T;
+    int batch, Sr;
+    const float* weights;
+    int s_begin;
+    const cplx* tables;
+    float* ic;  // [2][2][M][M] : ((rr*2 + rc)*M + kr)*M + kc, accumulated
+};
+
+template <int M, class Ctx>
+LITHO_HD void fast_load_tables(const cplx* tables, cplx* tab, const Ctx& ctx) {
+    for (int i = ctx.tid(); i < FastShape<M>::NTAB; i += ctx.bdim()) tab[i] = tables[i];
+    ctx.sync();
+}
+
+// grid.x = any (persistent over the batch*Sr*2 work items), block = ROW_THREADS
+template <int M, class Ctx>
+LITHO_HD void fast_rows_body(const FastRowsParams& P, const Ctx& ctx, cplx* smem) {
+    using F = FastShape<M>;
+    using Sh = typename F::Sh;
+    constexpr int TG = F::TG;
+    cplx* tab = smem;
+    fast_load_tables<M>(P.tables, tab, ctx);
+    const int grp = ctx.tid() / TG;
+    const int g = ctx.tid() - grp * TG;
+    cplx* ex = smem + F::NTAB_PAD + grp * Sh::SMEM_ELEMS;
+    const int total = P.batch * P.Sr * 2;
+    const int stride = ctx.gdx() * F::ROW_GROUPS;
+    const int rounds = (total + stride - 1) / stride;
+    const SmemTw<M> tw{tab};
+    const GroupSync<Ctx, F::WARP_GROUP> gs{ctx};
+
+    for (int it = 0; it < rounds; ++it) {
+        const int item = it * stride + ctx.bx() * F::ROW_GROUPS + grp;
+        const bool active = item < total;
+        const int r = item & 1;
+        const int li = item >> 1;
+        const int sl = active ? li / P.Sr : 0;
+        const int line = active ? li - sl * P.Sr : 0;
+        cplx v[32];
+        if (active) {
+            const int2_ sh = P.shifts[P.s_begin + sl];
+            const cplx* prow = P.pupil + (size_t)(P.pr0 + line) * P.pn + P.pc0;
+            // shifts are inside the plan's no-wrap range by contract; clamping keeps a violated
+            // contract memory-safe (the result is then wrong, never out of bounds)
+            const int mr = iclamp(P.pr0 + line + sh.x, 0, P.pn - 1);
+            const int mc = iclamp(P.pc0 + sh.y, 0, P.pn - P.Sc);
+            const cplx* mrow = P.mask + (size_t)mr * P.pn + mc;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+                const int u = g + TG * e;
+                cplx x = mk(0.f, 0.f);
+                if (u < P.Sc) {
+                    x = cmul(ldg_c(prow + u), ldg_c(mrow + u));
+                    if (r) x = cmul(x, tab[F::PRE_OFF + u]);
+                }
+                if (e == 0) {
+                    if (g == 0 && P.Sc > M) {  // rim input u = M folds onto slot 0 with w_2M^(r*M) = (-1)^r
+                        const cplx y = cmul(ldg_c(prow + M), ldg_c(mrow + M));
+                        x = r ? csub(x, y) : cadd(x, y);
+                    }
+                }
+                v[e] = x;
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = mk(0.f, 0.f);
+        }
+        fft_run<M, 32, false>(v, ex, 1, g, tw, gs);
+        if (active) {
+            cplx* dst = P.T + ((size_t)(sl * 2 + r) * P.Sr + line) * M + g;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) dst[TG * e] = v[e];
+        }
+    }
+}
+
+// grid.x = 2*M/CB column blocks (rc major), grid.y = 2 (rr), block = COL_THREADS
+template <int M, class Ctx>
+LITHO_HD void fast_cols_body(const FastColsParams& P, const Ctx& ctx, cplx* smem) {
+    using F = FastShape<M>;
+    constexpr int TG = F::TG;
+    constexpr int CB = F::CB;
+    cplx* tab = smem;
+    fast_load_tables<M>(P.tables, tab, ctx);
+    const int col = ctx.tid() % CB;
+    const int g = ctx.tid() / CB;
+    cplx* ex = smem + F::NTAB_PAD + col;
+    const int rr = ctx.by();
+    constexpr int NBLK = M / CB;
+    const int rc = ctx.bx() / NBLK;
+    const int kc = (ctx.bx() - rc * NBLK) * CB + col;
+    const SmemTw<M> tw{tab};
+    const GroupSync<Ctx, false> gs{ctx};
+
+    float acc[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) acc[e] = 0.f;
+
+    for (int sl = 0; sl < P.batch; ++sl) {
+        const cplx* src = P.T + ((size_t)(sl * 2 + rc) * P.Sr) * M + kc;
+        cplx v[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+            const int u = g + TG * e;
+            cplx x = mk(0.f, 0.f);
+            if (u < P.Sr) {
+                x = ldg_c(src + (size_t)u * M);
+                if (rr) x = cmul(x, tab[F::PRE_OFF + u]);
+            }
+            if (e == 0) {
+                if (g == 0 && P.Sr > M) {
+                    const cplx y = ldg_c(src + (size_t)M * M);
+                    x = rr ? csub(x, y) : cadd(x, y);
+                }
+            }
+            v[e] = x;
+        }
+        fft_run<M, 32, false>(v, ex, CB, g, tw, gs);
+        const float w = P.weights ? P.weights[P.s_begin + sl] : 1.f;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) acc[e] += w * cnorm2(v[e]);
+    }
+    float* dst = P.ic + ((size_t)(rr * 2 + rc) * M + g) * M + kc;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) dst[(size_t)(TG * e) * M] += acc[e];
+}
+
+// ----------------------------------------------------------------------------- rim lines
+// Frow[n + M] += sum_s w_s sum_{v1 - v2 = n} G_s[Sr-1][v1] * conj(G_s[0][v2])      (needs Sr == M+1)
+// Fcol[m + M] += sum_s w_s sum_{u1 - u2 = m} G_s[u1][Sc-1] * conj(G_s[u2][0])      (needs Sc == M+1)
+// These are the Fourier coefficients of sum_s |E_s|^2 at frequency +M along the row / column axis,
+// the only ones the Nc = 2M coarse grid cannot tell from their -M partners.
+// `ext` = non-zero extents of the pupil's first/last window row and column:
+//   {top_lo, top_hi, bot_lo, bot_hi, left_lo, left_hi, right_lo, right_hi}  (window coordinates)
+struct RimParams {
+    const cplx* pupil;
+    const cplx* mask;
+    int pn, pr0, pc0, Sr, Sc, M;
+    const int2_* shifts;
+    const float* weights;
+    int n_src;
+    int ext[8];
+    int do_row, do_col;
+    float* frow;  // (2M+1) complex, interleaved
+    float* fcol;
+};
+
+LITHO_HD void atomic_add_f(float* p, float v) {
+#if defined(__CUDA_ARCH__)
+    atomicAdd(p, v);
+#else
+    *p += v;
+#endif
+}
+
+// one CTA per source point; smem holds the two rim vectors (<= 2*(M+1) elements)
+template <class Ctx>
+LITHO_HD void rim_body(const RimParams& P, const Ctx& ctx, cplx* smem) {
+    const int s = ctx.bx();
+    const int2_ sh = P.shifts[s];
+    const float w = P.weights ? P.weights[s] : 1.f;
+    for (int axis = 0; axis < 2; ++axis) {
+        if (axis == 0 ? !P.do_row : !P.do_col) continue;
+        // "hi" vector: last window row (axis 0) / last window column (axis 1); "lo": first
+        const int hl = P.ext[axis * 4 + 2], hh = P.ext[axis * 4 + 3];  // bottom / right extents
+        const int ll = P.ext[axis * 4 + 0], lh = P.ext[axis * 4 + 1];  // top / left extents
+        const int nh = hh - hl + 1, nl = lh - ll + 1;
+        cplx* gh = smem;
+        cplx* gl = smem + nh;
+        ctx.sync();
+        for (int i = ctx.tid(); i < nh + nl; i += ctx.bdim()) {
+            const bool hi = i < nh;
+            const int t = hi ? hl + i : ll + (i - nh);            // position along the vector
+            const int fix = hi ? (axis == 0 ? P.Sr - 1 : P.Sc - 1) : 0;  // the fixed window coordinate
+            const int u = axis == 0 ? fix : t;                     // window row
+            const int v = axis == 0 ? t : fix;                     // window column
+            const cplx p = P.pupil[(size_t)(P.pr0 + u) * P.pn + P.pc0 + v];
+            const cplx m = P.mask[(size_t)iclamp(P.pr0 + u + sh.x, 0, P.pn - 1) * P.pn +
+                                  iclamp(P.pc0 + v + sh.y, 0, P.pn - 1)];
+            smem[i] = cmul(p, m);
+        }
+        ctx.sync();
+        // correlation lags n = (hl + a) - (ll + b), a in [0,nh), b in [0,nl)
+        const int nlag = nh + nl - 1;
+        float* F = axis == 0 ? P.frow : P.fcol;
+        for (int li = ctx.tid(); li < nlag; li += ctx.bdim()) {
+            const int d = li - (nl - 1);  // a - b
+            const int b0 = d < 0 ? -d : 0;
+            const int b1 = (nh - d) < nl ? (nh - d) : nl;
+            cplx acc = mk(0.f, 0.f);
+            for (int b = b0; b < b1; ++b) acc = cadd(acc, cmul(gh[b + d], cconj(gl[b])));
+            const int n = (hl - ll) + d;
+            atomic_add_f(F + 2 * (n + P.M), w * acc.x);
+            atomic_add_f(F + 2 * (n + P.M) + 1, w * acc.y);
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------- coarse -> fine
+// Spectrum assembly: Fhat is the centred Nc x Nc DFT of the coarse intensity (index m+K, K = Nc/2 = M,
+// m in [-K,K)); out is (Nc+1) x (Nc+1) with m,n in [-K,K].  Interior copied; the +-K lines come from
+// the rim sums when they exist, otherwise the (then unaliased) -K bin is split... no energy: zero.
+struct AssembleParams {
+    const cplx* fhat;   // [Nc][Nc]
+    const float* frow;  // F[K][n], n = -K..K
+    const float* fcol;  // F[m][K], m = -K..K
+    int Nc, do_row, do_col;
+    cplx* out;          // [Nc+1][Nc+1]
+};
+
+LITHO_HD cplx rim_get(const float* f, int idx) { return mk(f[2 * idx], f[2 * idx + 1]); }
+
+LITHO_HD void assemble_elem(const AssembleParams& P, int i, int j) {
+    const int K = P.Nc / 2;
+    const int m = i - K, n = j - K;  // in [-K, K]
+    cplx val = mk(0.f, 0.f);
+    const bool mr = (m == K || m == -K), nr = (n == K || n == -K);
+    if (!mr && !nr) {
+        val = P.fhat[(size_t)i * P.Nc + j];
+    } else if (mr && P.do_row) {
+        // F[K][n] = frow[n];  F[-K][n] = conj(F[K][-n])
+        val = (m == K) ? rim_get(P.frow, n + K) : cconj(rim_get(P.frow, -n + K));
+    } else if (nr && P.do_col) {
+        val = (n == K) ? rim_get(P.fcol, m + K) : cconj(rim_get(P.fcol, -m + K));
+    } else {
+        // no rim energy on this line: the -K bin of the DFT is exact (and ~0), +K is zero
+        if (m != K && n != K) val = P.fhat[(size_t)i * P.Nc + j];
+    }
+    P.out[(size_t)i * (P.Nc + 1) + j] = val;
+}
+
+}  // namespace litho

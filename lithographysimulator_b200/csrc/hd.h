@@ -73,7 +73,9 @@ struct DevCtx {
     __device__ __forceinline__ int bx() const { return blockIdx.x; }
     __device__ __forceinline__ int by() const { return blockIdx.y; }
     __device__ __forceinline__ int bz() const { return blockIdx.z; }
+    __device__ __forceinline__ int gdx() const { return gridDim.x; }
     __device__ __forceinline__ void sync() const { __syncthreads(); }
+    __device__ __forceinline__ void sync_warp() const { __syncwarp(); }
 };
 #endif
 

@@ -104,6 +104,57 @@ struct UnpermParams {
     float* out;
 };
 
+// non-zero extents of the first/last bbox row and column of the pupil (absolute grid indices):
+// ext = {row r0: cmin,cmax | row r1: cmin,cmax | col c0: rmin,rmax | col c1: rmin,rmax}
+struct ExtParams {
+    const cplx* pupil;
+    int pn, r0, r1, c0, c1;
+    int* ext;
+};
+
+template <class Ctx>
+LITHO_HD void ext_body(const ExtParams& P, const Ctx& ctx) {
+    for (int i = ctx.tid(); i < P.pn; i += ctx.bdim()) {
+        const cplx a = P.pupil[(size_t)P.r0 * P.pn + i], b = P.pupil[(size_t)P.r1 * P.pn + i];
+        const cplx c = P.pupil[(size_t)i * P.pn + P.c0], d = P.pupil[(size_t)i * P.pn + P.c1];
+        if (a.x != 0.f || a.y != 0.f) { atomic_min_i(P.ext + 0, i); atomic_max_i(P.ext + 1, i); }
+        if (b.x != 0.f || b.y != 0.f) { atomic_min_i(P.ext + 2, i); atomic_max_i(P.ext + 3, i); }
+        if (c.x != 0.f || c.y != 0.f) { atomic_min_i(P.ext + 4, i); atomic_max_i(P.ext + 5, i); }
+        if (d.x != 0.f || d.y != 0.f) { atomic_min_i(P.ext + 6, i); atomic_max_i(P.ext + 7, i); }
+    }
+}
+
+struct ShiftBoundsParams {
+    const int2_* shifts;
+    int n;
+    int* out;  // {min d0, max d0, min d1, max d1}
+};
+
+template <class Ctx>
+LITHO_HD void shift_bounds_body(const ShiftBoundsParams& P, const Ctx& ctx) {
+    int lo0 = INT32_MAX, hi0 = INT32_MIN, lo1 = INT32_MAX, hi1 = INT32_MIN;
+    for (int i = ctx.bx() * ctx.bdim() + ctx.tid(); i < P.n; i += ctx.bdim() * ctx.gdx()) {
+        const int2_ s = P.shifts[i];
+        lo0 = s.x < lo0 ? s.x : lo0; hi0 = s.x > hi0 ? s.x : hi0;
+        lo1 = s.y < lo1 ? s.y : lo1; hi1 = s.y > hi1 ? s.y : hi1;
+    }
+    if (hi0 >= lo0) {
+        atomic_min_i(P.out + 0, lo0); atomic_max_i(P.out + 1, hi0);
+        atomic_min_i(P.out + 2, lo1); atomic_max_i(P.out + 3, hi1);
+    }
+}
+
+// coarse plane [2][2][M][M] -> natural Nc x Nc plane (o = 2k + r on both axes)
+struct CoarseUnpermParams {
+    const float* ic;
+    int M;
+    float* out;  // [2M][2M]
+};
+LITHO_HD void coarse_unperm_elem(const CoarseUnpermParams& P, int a, int b) {
+    const int M = P.M;
+    P.out[(size_t)a * (2 * M) + b] = P.ic[((size_t)((a & 1) * 2 + (b & 1)) * M + (a >> 1)) * M + (b >> 1)];
+}
+
 #if !defined(LITHO_EMU)
 __global__ void __launch_bounds__(256) fma_probe_kernel(float* out, int iters) {
     float a[16];
@@ -120,6 +171,20 @@ __global__ void __launch_bounds__(256) fma_probe_kernel(float* out, int iters) {
     if (s == 12345.678f) out[0] = s;  // never true: keeps the loop alive without memory traffic
 }
 __global__ void bbox_kernel(const __grid_constant__ BBoxParams P) { bbox_body(P, DevCtx{}); }
+__global__ void ext_kernel(const __grid_constant__ ExtParams P) { ext_body(P, DevCtx{}); }
+__global__ void shift_bounds_kernel(const __grid_constant__ ShiftBoundsParams P) { shift_bounds_body(P, DevCtx{}); }
+__global__ void rim_kernel(const __grid_constant__ RimParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    rim_body(P, DevCtx{}, reinterpret_cast<cplx*>(smem_raw));
+}
+__global__ void coarse_unperm_kernel(const __grid_constant__ CoarseUnpermParams P) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < 2 * P.M) coarse_unperm_elem(P, blockIdx.y, b);
+}
+__global__ void assemble_kernel(const __grid_constant__ AssembleParams P) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j <= P.Nc) assemble_elem(P, blockIdx.y, j);
+}
 __global__ void finalize_kernel(const __grid_constant__ FinalizeParams P) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
@@ -204,9 +269,61 @@ struct litho_plan {
     cplx* twL;  // device: w_L[i] = exp(+2*pi*i*i/L)
     int rows_fpc, cols_cb;
     int default_batch;
+    // fast path (fast_kernels.h): coarse grid Nc = 2*Mf, q = N/Nc
+    int path;        // 1 = generic fine grid, 2 = fast coarse grid
+    int Mf, Nc, q;
+    int rim_row, rim_col;  // Sr == Mf+1 / Sc == Mf+1: the +-Mf frequency line needs the rim sums
+    int ext[8];      // non-zero extents of the first/last window row and column (window coordinates)
+    cplx* tables;    // device twiddle tables of the fast kernels (owned by the plan)
+    int n_sm;
 };
 
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+static int dispatch_fast_rows(int M, const FastRowsParams& P, int gx, litho_stream_t st) {
+    switch (M) {
+#define X(m) case m: return launch_fast_rows_m<m>(P, gx, st);
+        LITHO_FOR_EACH_FAST_M(X)
+#undef X
+    }
+    return -1;
+}
+static int dispatch_fast_cols(int M, const FastColsParams& P, litho_stream_t st) {
+    switch (M) {
+#define X(m) case m: return launch_fast_cols_m<m>(P, st);
+        LITHO_FOR_EACH_FAST_M(X)
+#undef X
+    }
+    return -1;
+}
+static int dispatch_fast_ntab(int M) {
+    switch (M) {
+#define X(m) case m: return fast_ntab_m<m>();
+        LITHO_FOR_EACH_FAST_M(X)
+#undef X
+    }
+    return -1;
+}
+
+// host mirror of FastShape<M>: table layout {pre[0..M], tw1[(t-1)*32+k], tw2[(t-1)*NS2+k]}
+static std::vector<cplx> build_fast_tables(int M) {
+    int lg = 0;
+    for (int m = M; m > 1; m >>= 1) ++lg;
+    const int R1 = lg > 5 ? (lg - 5 >= 5 ? 32 : (1 << (lg - 5))) : 1;
+    const int R2 = lg > 10 ? (1 << (lg - 10)) : 1;
+    const int NS1 = 32, NS2 = 32 * R1;
+    std::vector<cplx> t;
+    auto push = [&](double num, double den) {
+        const double a = 2.0 * M_PI * num / den;
+        t.push_back(mk((float)cos(a), (float)sin(a)));
+    };
+    for (int u = 0; u <= M; ++u) push((double)u, 2.0 * M);
+    for (int tt = 1; tt < R1; ++tt)
+        for (int k = 0; k < NS1; ++k) push((double)tt * k, (double)NS1 * R1);
+    for (int tt = 1; tt < R2; ++tt)
+        for (int k = 0; k < NS2; ++k) push((double)tt * k, (double)NS2 * R2);
+    return t;
+}
 
 static int dispatch_shape(int M, int* fpc, int* cb) {
     switch (M) {
@@ -288,8 +405,71 @@ int litho_pupil_bbox(const void* pupil, int pn, int* bbox_host, void* stream) {
     return LITHO_OK;
 }
 
+int litho_pupil_support(const void* pupil, int pn, int* support_host, void* stream) {
+    if (!support_host) return fail(LITHO_ERR_ARG, "pupil_support: null argument");
+    int rc = litho_pupil_bbox(pupil, pn, support_host, stream);
+    if (rc) return rc;
+    const int r0 = support_host[0], r1 = support_host[1], c0 = support_host[2], c1 = support_host[3];
+    if (r1 < r0) {
+        for (int i = 4; i < 12; ++i) support_host[i] = (i & 1) ? -1 : 0;
+        return LITHO_OK;
+    }
+    litho_stream_t st = (litho_stream_t)stream;
+    int* dext = nullptr;
+    BE_CHECK(be_malloc((void**)&dext, 8 * sizeof(int)));
+    int init[8] = {pn, -1, pn, -1, pn, -1, pn, -1};
+    rc = be_h2d(dext, init, sizeof(init), st);
+    if (rc == 0) {
+        ExtParams P{(const cplx*)pupil, pn, r0, r1, c0, c1, dext};
+#if defined(LITHO_EMU)
+        litho_emu::launch(1, 1, 1, 32, 0, [&](const litho_emu::EmuCtx& c, char*) { ext_body(P, c); });
+#else
+        ext_kernel<<<1, 1024, 0, st>>>(P);
+        rc = (int)cudaGetLastError();
+#endif
+    }
+    if (rc == 0) rc = be_d2h_sync(support_host + 4, dext, 8 * sizeof(int), st);
+    be_free(dext);
+    if (rc != 0) return fail(LITHO_ERR_CUDA, std::string("pupil_support: ") + be_errstr(rc));
+    return LITHO_OK;
+}
+
+int litho_shift_bounds(const int32_t* shifts, int n_src, int* bounds_host, void* stream) {
+    if (!bounds_host || n_src < 0 || (n_src > 0 && !shifts)) return fail(LITHO_ERR_ARG, "shift_bounds: bad argument");
+    bounds_host[0] = bounds_host[2] = 0;
+    bounds_host[1] = bounds_host[3] = 0;
+    if (n_src == 0) return LITHO_OK;
+    litho_stream_t st = (litho_stream_t)stream;
+    int* d = nullptr;
+    BE_CHECK(be_malloc((void**)&d, 4 * sizeof(int)));
+    int init[4] = {INT32_MAX, INT32_MIN, INT32_MAX, INT32_MIN};
+    int rc = be_h2d(d, init, sizeof(init), st);
+    if (rc == 0) {
+        ShiftBoundsParams P{(const int2_*)shifts, n_src, d};
+#if defined(LITHO_EMU)
+        litho_emu::launch(1, 1, 1, 32, 0, [&](const litho_emu::EmuCtx& c, char*) { shift_bounds_body(P, c); });
+#else
+        shift_bounds_kernel<<<(n_src + 255) / 256 > 64 ? 64 : (n_src + 255) / 256, 256, 0, st>>>(P);
+        rc = (int)cudaGetLastError();
+#endif
+    }
+    if (rc == 0) rc = be_d2h_sync(bounds_host, d, 4 * sizeof(int), st);
+    be_free(d);
+    if (rc != 0) return fail(LITHO_ERR_CUDA, std::string("shift_bounds: ") + be_errstr(rc));
+    return LITHO_OK;
+}
+
 int litho_plan_create(int pn, int N, const int* bbox, int flags, litho_plan_t** out) {
-    (void)flags;
+    if (!bbox) return fail(LITHO_ERR_ARG, "plan_create: null argument");
+    // without measured extents the rim lines are assumed to span the whole window (correct, just slower)
+    int sup[12];
+    for (int i = 0; i < 4; ++i) sup[i] = bbox[i];
+    sup[4] = sup[6] = bbox[2]; sup[5] = sup[7] = bbox[3];   // first/last row: columns c0..c1
+    sup[8] = sup[10] = bbox[0]; sup[9] = sup[11] = bbox[1]; // first/last column: rows r0..r1
+    return litho_plan_create_ex(pn, N, sup, flags, out);
+}
+
+int litho_plan_create_ex(int pn, int N, const int* bbox, int flags, litho_plan_t** out) {
     if (!out || !bbox) return fail(LITHO_ERR_ARG, "plan_create: null argument");
     if (pn < 2 || (pn & 1)) return fail(LITHO_ERR_ARG, "plan_create: pixelNumber must be even and >= 2 (odd grids make the reference transform length N-1)");
     if (!is_pow2(N) || N > 16384 || N < 16) return fail(LITHO_ERR_ARG, "plan_create: N must be a power of two in [16,16384]");
@@ -322,7 +502,49 @@ int litho_plan_create(int pn, int N, const int* bbox, int flags, litho_plan_t** 
         return fail(LITHO_ERR_CUDA, std::string("plan_create: twiddle table: ") + be_errstr(rc));
     }
     // batch: keep T for one launch pair around 64 MB (L2-resident on B200), at least 1, at most 16
-    const size_t per = (size_t)p->zp.R * p->Sr * p->zp.Wr * sizeof(cplx);
+    size_t per = (size_t)p->zp.R * p->Sr * p->zp.Wr * sizeof(cplx);
+    // ---- fast path eligibility: even window fit S <= Mf+1, coarse grid Nc = 2*Mf no finer than N ----
+    p->path = 1; p->tables = nullptr; p->Mf = p->Nc = p->q = 0; p->rim_row = p->rim_col = 0;
+    p->n_sm = 148;
+#if !defined(LITHO_EMU)
+    {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            p->n_sm = n;
+    }
+#endif
+    int Mf = 32;
+    while (Mf < S - 1) Mf <<= 1;
+    if (!(flags & LITHO_PLAN_GENERIC) && Mf <= 4096 && 2 * Mf <= N) {
+        std::vector<cplx> tab = build_fast_tables(Mf);
+        if ((int)tab.size() != dispatch_fast_ntab(Mf)) {
+            delete p;
+            return fail(LITHO_ERR_ARG, "plan_create: internal table layout mismatch");
+        }
+        rc = be_malloc((void**)&p->tables, tab.size() * sizeof(cplx));
+        if (rc == 0) rc = be_h2d(p->tables, tab.data(), tab.size() * sizeof(cplx), 0);
+#if !defined(LITHO_EMU)
+        if (rc == 0) rc = (int)cudaStreamSynchronize(0);
+#endif
+        if (rc != 0) {
+            if (p->tables) be_free(p->tables);
+            delete p;
+            return fail(LITHO_ERR_CUDA, std::string("plan_create: fast tables: ") + be_errstr(rc));
+        }
+        p->path = 2; p->Mf = Mf; p->Nc = 2 * Mf; p->q = N / (2 * Mf);
+        p->rim_row = (p->Sr == Mf + 1);
+        p->rim_col = (p->Sc == Mf + 1);
+        // extents in window coordinates, clamped to the window
+        const int* e = bbox + 4;
+        auto clampi = [](int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); };
+        p->ext[0] = clampi(e[0] - c0, 0, p->Sc - 1); p->ext[1] = clampi(e[1] - c0, 0, p->Sc - 1);  // first row
+        p->ext[2] = clampi(e[2] - c0, 0, p->Sc - 1); p->ext[3] = clampi(e[3] - c0, 0, p->Sc - 1);  // last row
+        p->ext[4] = clampi(e[4] - r0, 0, p->Sr - 1); p->ext[5] = clampi(e[5] - r0, 0, p->Sr - 1);  // first column
+        p->ext[6] = clampi(e[6] - r0, 0, p->Sr - 1); p->ext[7] = clampi(e[7] - r0, 0, p->Sr - 1);  // last column
+        per = (size_t)2 * p->Sr * Mf * sizeof(cplx);
+    }
+    // batch: keep T for one launch pair around 64 MB (L2-resident on B200), at least 1, at most 16
     int b = (int)((64u << 20) / (per ? per : 1));
     p->default_batch = b < 1 ? 1 : (b > 16 ? 16 : b);
     *out = p;
@@ -331,11 +553,19 @@ int litho_plan_create(int pn, int N, const int* bbox, int flags, litho_plan_t** 
 
 void litho_plan_destroy(litho_plan_t* p) {
     if (!p) return;
-    delete p;  // the twiddle table belongs to the process-wide cache
+    if (p->tables) be_free(p->tables);
+    delete p;  // the w_L twiddle table belongs to the process-wide cache
 }
 
 static uint64_t intensity_elems(const litho_plan* p) {
+    if (p->path == 2)  // coarse plane [2][2][Mf][Mf] + the two rim lines (2*Mf+1 complex each)
+        return (uint64_t)4 * p->Mf * p->Mf + (uint64_t)4 * (2 * p->Mf + 1);
     return (uint64_t)p->zp.R * p->zp.R * p->zp.Wr * p->zp.Wr;
+}
+
+static float* rim_row_ptr(const litho_plan* p, float* intensity) { return intensity + (size_t)4 * p->Mf * p->Mf; }
+static float* rim_col_ptr(const litho_plan* p, float* intensity) {
+    return intensity + (size_t)4 * p->Mf * p->Mf + (size_t)2 * (2 * p->Mf + 1);
 }
 
 int litho_plan_get_info(const litho_plan_t* p, litho_plan_info_t* info) {
@@ -343,16 +573,76 @@ int litho_plan_get_info(const litho_plan_t* p, litho_plan_info_t* info) {
     info->pn = p->pn; info->N = p->N;
     memcpy(info->bbox, p->bbox, sizeof(p->bbox));
     info->L = p->zp.L; info->M = p->zp.M; info->R = p->zp.R; info->Wr = p->zp.Wr;
-    info->path = 1;
+    info->path = p->path;
+    if (p->path == 2) {
+        info->L = p->Nc; info->M = p->Mf; info->R = 2; info->Wr = p->Mf;
+    }
     info->default_batch = p->default_batch;
     info->intensity_elems = intensity_elems(p);
+    // shifts for which roll() does not wrap the pupil window (precondition of the fast path)
+    info->shift_range[0] = -p->bbox[0]; info->shift_range[1] = p->pn - 1 - p->bbox[1];
+    info->shift_range[2] = -p->bbox[2]; info->shift_range[3] = p->pn - 1 - p->bbox[3];
     return LITHO_OK;
+}
+
+static size_t align16(size_t b) { return (b + 15) / 16 * 16; }
+
+// T of the generic kernels (also used by litho_fft_field on any plan)
+static size_t generic_t_bytes(const litho_plan* p, int batch) {
+    return (size_t)batch * p->zp.R * p->Sr * p->zp.Wr * sizeof(cplx);
 }
 
 size_t litho_plan_workspace_bytes(const litho_plan_t* p, int batch) {
     if (!p) return 0;
     if (batch <= 0) batch = p->default_batch;
-    return (size_t)batch * p->zp.R * p->Sr * p->zp.Wr * sizeof(cplx);
+    if (p->path == 2) {
+        const size_t fast = (size_t)batch * 2 * p->Sr * p->Mf * sizeof(cplx);
+        const size_t gen1 = generic_t_bytes(p, 1);
+        return fast > gen1 ? fast : gen1;
+    }
+    return generic_t_bytes(p, batch);
+}
+
+// coarse -> fine interpolation buffers of the fast path (see fine_plane_fast)
+struct FinalizeLayout {
+    size_t a_off, t1_off, fhat_off, spec_off, t2_off, fine_off, total;
+    ZoomPlan z1, z2;
+    AxisOut o1, o2;
+    int fpc1, cb1, fpc2, cb2;
+};
+
+static int finalize_layout(const litho_plan* p, FinalizeLayout* L) {
+    memset(L, 0, sizeof(*L));
+    const int pn = p->pn;
+    size_t off = 0;
+    if (p->path == 2 && p->q > 1) {
+        const int Nc = p->Nc, N = p->N;
+        // step 1: centred forward DFT of the Nc x Nc coarse plane (one length-Nc FFT per line)
+        L->z1.L = Nc; L->z1.M = Nc; L->z1.R = 1; L->z1.Wr = Nc;
+        L->o1.W = Nc; L->o1.center = Nc / 2;
+        // step 2: inverse zoom of the (Nc+1)^2 spectrum to the pn centre pixels of the N grid
+        L->z2.L = N; L->z2.M = Nc; L->z2.R = N / Nc; L->z2.Wr = (pn + L->z2.R - 1) / L->z2.R;
+        L->o2.W = pn; L->o2.center = pn / 2;
+        if (dispatch_shape(Nc, &L->fpc1, &L->cb1)) return 1;
+        L->fpc2 = L->fpc1; L->cb2 = L->cb1;
+        L->a_off = off;    off += align16((size_t)Nc * Nc * sizeof(float));
+        L->t1_off = off;   off += align16((size_t)Nc * Nc * sizeof(cplx));
+        L->fhat_off = off; off += align16((size_t)Nc * Nc * sizeof(cplx));
+        L->spec_off = off; off += align16((size_t)(Nc + 1) * (Nc + 1) * sizeof(cplx));
+        L->t2_off = off;   off += align16((size_t)L->z2.R * (Nc + 1) * L->z2.Wr * sizeof(cplx));
+    }
+    L->fine_off = off;
+    off += align16((size_t)pn * pn * sizeof(float));
+    L->total = off;
+    return 0;
+}
+
+size_t litho_plan_finalize_workspace_bytes(const litho_plan_t* p) {
+    if (!p) return 0;
+    if (p->path != 2 || p->q == 1) return 16;  // nothing to stage
+    FinalizeLayout L;
+    if (finalize_layout(p, &L)) return 0;
+    return L.total;
 }
 
 static AxisIn axis_in(int first, int pn, int S) {
@@ -380,6 +670,47 @@ int litho_abbe_fft_accumulate_ex(const litho_plan_t* p, const void* maskFT, cons
     if (!workspace || workspace_bytes < litho_plan_workspace_bytes(p, batch))
         return fail(LITHO_ERR_WORKSPACE, "accumulate: workspace too small for the requested batch");
     litho_stream_t st = (litho_stream_t)stream;
+    if (p->path == 2) {
+        // fast coarse-grid kernels; the caller guarantees shifts inside plan.shift_range (no wrap)
+        FastRowsParams fr;
+        memset(&fr, 0, sizeof(fr));
+        fr.pupil = (const cplx*)pupil; fr.mask = (const cplx*)maskFT; fr.pn = p->pn;
+        fr.pr0 = p->bbox[0]; fr.pc0 = p->bbox[2]; fr.Sr = p->Sr; fr.Sc = p->Sc;
+        fr.shifts = (const int2_*)shifts; fr.tables = p->tables; fr.T = (cplx*)workspace;
+        FastColsParams fc;
+        memset(&fc, 0, sizeof(fc));
+        fc.T = (const cplx*)workspace; fc.Sr = p->Sr; fc.weights = weights; fc.tables = p->tables;
+        fc.ic = intensity;
+        for (int s0 = 0; s0 < n_src; s0 += batch) {
+            const int nb = (n_src - s0) < batch ? (n_src - s0) : batch;
+            fr.s_begin = s0; fr.batch = nb;
+            fc.s_begin = s0; fc.batch = nb;
+            if (phases & 1) BE_CHECK(dispatch_fast_rows(p->Mf, fr, p->n_sm * 2, st));
+            if (phases & 2) BE_CHECK(dispatch_fast_cols(p->Mf, fc, st));
+        }
+        if ((phases & 2) && p->q > 1 && (p->rim_row || p->rim_col)) {
+            RimParams rm;
+            memset(&rm, 0, sizeof(rm));
+            rm.pupil = (const cplx*)pupil; rm.mask = (const cplx*)maskFT; rm.pn = p->pn;
+            rm.pr0 = p->bbox[0]; rm.pc0 = p->bbox[2]; rm.Sr = p->Sr; rm.Sc = p->Sc; rm.M = p->Mf;
+            rm.shifts = (const int2_*)shifts; rm.weights = weights; rm.n_src = n_src;
+            memcpy(rm.ext, p->ext, sizeof(rm.ext));
+            rm.do_row = p->rim_row; rm.do_col = p->rim_col;
+            rm.frow = rim_row_ptr(p, intensity); rm.fcol = rim_col_ptr(p, intensity);
+            const int n_row = (p->ext[3] - p->ext[2] + 1) + (p->ext[1] - p->ext[0] + 1);
+            const int n_col = (p->ext[7] - p->ext[6] + 1) + (p->ext[5] - p->ext[4] + 1);
+            const size_t smem = (size_t)(n_row > n_col ? n_row : n_col) * sizeof(cplx);
+#if defined(LITHO_EMU)
+            litho_emu::launch(n_src, 1, 1, 64, smem, [&](const litho_emu::EmuCtx& c, char* s) { rim_body(rm, c, (cplx*)s); });
+#else
+            if (smem > 48 * 1024)
+                BE_CHECK((int)cudaFuncSetAttribute(rim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            rim_kernel<<<n_src, 256, smem, st>>>(rm);
+            BE_CHECK((int)cudaGetLastError());
+#endif
+        }
+        return LITHO_OK;
+    }
     const int R = p->zp.R, M = p->zp.M;
 
     RowsParams rp;
@@ -414,10 +745,92 @@ int litho_abbe_fft_accumulate_ex(const litho_plan_t* p, const void* maskFT, cons
 
 static PermView perm_view(const litho_plan* p, const float* intensity) {
     PermView v;
+    memset(&v, 0, sizeof(v));
     v.iperm = intensity;
     v.outr = p->out; v.outc = p->out;
     v.Rr = p->zp.R; v.Rc = p->zp.R; v.Wrr = p->zp.Wr; v.Wrc = p->zp.Wr;
+    if (p->path == 2) {  // q == 1: the coarse grid is the fine grid, read it in place
+        v.mode = 2; v.Mc = p->Mf; v.center = p->pn / 2;
+    }
     return v;
+}
+
+// Fast path with q > 1: exact (spectral) interpolation of the coarse intensity to the pn centre pixels
+// of the reference's N grid.  Leaves the natural pn x pn plane at ws + L.fine_off and returns a view on it.
+//   1. coarse plane -> natural order                      (coarse_unperm)
+//   2. centred forward DFT, scaled 1/Nc^2                 (generic zoom kernels, conjugating epilogue)
+//   3. (Nc+1)^2 spectrum with the +-Mf lines from the rim sums   (assemble)
+//   4. inverse zoom DFT of length N to the pn centre pixels, real part   (generic zoom kernels)
+static int fine_plane_fast(const litho_plan* p, const float* intensity, void* workspace, size_t workspace_bytes,
+                           litho_stream_t st, PermView* view) {
+    FinalizeLayout L;
+    if (finalize_layout(p, &L)) return fail(LITHO_ERR_ARG, "finalize: unsupported coarse grid");
+    if (!workspace || workspace_bytes < L.total) return fail(LITHO_ERR_WORKSPACE, "finalize: workspace too small");
+    char* ws = (char*)workspace;
+    float* A = (float*)(ws + L.a_off);
+    cplx* T1 = (cplx*)(ws + L.t1_off);
+    cplx* fhat = (cplx*)(ws + L.fhat_off);
+    cplx* spec = (cplx*)(ws + L.spec_off);
+    cplx* T2 = (cplx*)(ws + L.t2_off);
+    float* fine = (float*)(ws + L.fine_off);
+    const int Nc = p->Nc, pn = p->pn, N = p->N;
+    cplx *tw1 = nullptr, *tw2 = nullptr;
+    BE_CHECK(get_twiddles(Nc, &tw1));
+    BE_CHECK(get_twiddles(N, &tw2));
+
+    CoarseUnpermParams cu{intensity, p->Mf, A};
+#if defined(LITHO_EMU)
+    for (int a = 0; a < Nc; ++a)
+        for (int b = 0; b < Nc; ++b) coarse_unperm_elem(cu, a, b);
+#else
+    coarse_unperm_kernel<<<dim3((Nc + 255) / 256, Nc, 1), 256, 0, st>>>(cu);
+    BE_CHECK((int)cudaGetLastError());
+#endif
+    const int BIG = 1 << 30;
+    {   // step 2: Fhat[m][n] = (1/Nc^2) sum_ab A[a][b] exp(-2 pi i (m a + n b)/Nc), m,n in [-Nc/2, Nc/2)
+        AxisIn ax; ax.first = 0; ax.period = BIG; ax.center = 0; ax.S = Nc;
+        RowsParams rp; memset(&rp, 0, sizeof(rp));
+        rp.real_in = A; rp.in_pitch = Nc; rp.lines = Nc; rp.ax = ax; rp.out = L.o1; rp.plan = L.z1; rp.twL = tw1; rp.T = T1;
+        ColsParams cp; memset(&cp, 0, sizeof(cp));
+        cp.T = T1; cp.batch = 1; cp.Rc = 1; cp.Wrc = Nc; cp.outc = L.o1; cp.ax = ax; cp.out = L.o1; cp.plan = L.z1;
+        cp.twL = tw1; cp.field = fhat; cp.field_pitch = Nc; cp.conj_out = 1;
+        cp.scale = (float)(1.0 / ((double)Nc * (double)Nc));
+        BE_CHECK(dispatch_rows(Nc, ROW_REAL_PLANE, rp, (Nc + L.fpc1 - 1) / L.fpc1, 1, st));
+        BE_CHECK(dispatch_cols(Nc, EPI_FIELD, cp, (Nc + L.cb1 - 1) / L.cb1, 1, st));
+    }
+    AssembleParams as;
+    as.fhat = fhat; as.frow = rim_row_ptr(p, const_cast<float*>(intensity));
+    as.fcol = rim_col_ptr(p, const_cast<float*>(intensity));
+    as.Nc = Nc; as.do_row = p->rim_row; as.do_col = p->rim_col; as.out = spec;
+#if defined(LITHO_EMU)
+    for (int i = 0; i <= Nc; ++i)
+        for (int j = 0; j <= Nc; ++j) assemble_elem(as, i, j);
+#else
+    assemble_kernel<<<dim3((Nc + 1 + 255) / 256, Nc + 1, 1), 256, 0, st>>>(as);
+    BE_CHECK((int)cudaGetLastError());
+#endif
+    {   // step 4: fine[i][j] = Re sum_{m,n=-K..K} spec[m][n] exp(+2 pi i (m i' + n j')/N), i' = i - pn/2
+        AxisIn ax; ax.first = 0; ax.period = BIG; ax.center = Nc / 2; ax.S = Nc + 1;
+        const int R = L.z2.R;
+        RowsParams rp; memset(&rp, 0, sizeof(rp));
+        rp.cplx_in = spec; rp.in_pitch = Nc + 1; rp.lines = Nc + 1; rp.ax = ax; rp.out = L.o2; rp.plan = L.z2;
+        rp.twL = tw2; rp.T = T2;
+        ColsParams cp; memset(&cp, 0, sizeof(cp));
+        cp.T = T2; cp.batch = 1; cp.Rc = R; cp.Wrc = L.z2.Wr; cp.outc = L.o2; cp.ax = ax; cp.out = L.o2; cp.plan = L.z2;
+        cp.twL = tw2; cp.real_out = fine; cp.field_pitch = pn; cp.conj_out = 0; cp.scale = 1.f;
+        BE_CHECK(dispatch_rows(Nc, ROW_CPLX_PLANE, rp, ((Nc + 1) * R + L.fpc2 - 1) / L.fpc2, 1, st));
+        BE_CHECK(dispatch_cols(Nc, EPI_FIELD, cp, R * ((L.z2.Wr + L.cb2 - 1) / L.cb2), R, st));
+    }
+    memset(view, 0, sizeof(*view));
+    view->mode = 1; view->iperm = fine; view->pitch = pn;
+    return LITHO_OK;
+}
+
+static int source_view(const litho_plan* p, const float* intensity, void* workspace, size_t workspace_bytes,
+                       litho_stream_t st, PermView* view) {
+    if (p->path == 2 && p->q > 1) return fine_plane_fast(p, intensity, workspace, workspace_bytes, st, view);
+    *view = perm_view(p, intensity);
+    return LITHO_OK;
 }
 
 // imageformation.py:71-75 size arithmetic (python semantics: floor, round-half-even, floor division)
@@ -437,10 +850,12 @@ int litho_fft_output_side(int pn, double eps) {
     return os;
 }
 
-int litho_abbe_fft_finalize(const litho_plan_t* p, const float* intensity, double eps, float* out, void* stream) {
+int litho_abbe_fft_finalize(const litho_plan_t* p, const float* intensity, double eps, float* out, void* workspace,
+                            size_t workspace_bytes, void* stream) {
     if (!p || !intensity || !out || !(eps > 0)) return fail(LITHO_ERR_ARG, "finalize: bad argument");
     FinalizeParams F;
-    F.in = perm_view(p, intensity);
+    int rcv = source_view(p, intensity, workspace, workspace_bytes, (litho_stream_t)stream, &F.in);
+    if (rcv) return rcv;
     F.pn = p->pn;
     post_sizes(p->pn, eps, &F.side, &F.pW, &F.out_side);
     if (F.out_side <= 0) return fail(LITHO_ERR_ARG, "finalize: empty output");
@@ -458,10 +873,12 @@ int litho_abbe_fft_finalize(const litho_plan_t* p, const float* intensity, doubl
     return LITHO_OK;
 }
 
-int litho_abbe_fft_unpermute(const litho_plan_t* p, const float* intensity, float* out, void* stream) {
+int litho_abbe_fft_unpermute(const litho_plan_t* p, const float* intensity, float* out, void* workspace,
+                             size_t workspace_bytes, void* stream) {
     if (!p || !intensity || !out) return fail(LITHO_ERR_ARG, "unpermute: null argument");
     UnpermParams U;
-    U.in = perm_view(p, intensity);
+    int rcv = source_view(p, intensity, workspace, workspace_bytes, (litho_stream_t)stream, &U.in);
+    if (rcv) return rcv;
     U.pn = p->pn;
     U.out = out;
 #if defined(LITHO_EMU)

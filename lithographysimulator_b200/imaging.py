@@ -55,7 +55,7 @@ class AbbeEngine:
         self.device = device
         self.lib = _native.device_lib()
         self._plans: dict = {}
-        self._workspace: torch.Tensor | None = None
+        self._workspaces: dict = {}
 
     @classmethod
     def get(cls, device) -> "AbbeEngine":
@@ -73,17 +73,32 @@ class AbbeEngine:
     def pupil_bbox(self, pupil_d: torch.Tensor):
         return self.lib.pupil_bbox(pupil_d.data_ptr(), pupil_d.shape[0], self.stream())
 
-    def plan(self, pn: int, N: int, bbox) -> _native.Plan:
-        key = (pn, N, tuple(bbox))
+    def pupil_support(self, pupil_d: torch.Tensor):
+        """bbox + rim extents of the non-zero pupil samples (12 ints, one device sync)."""
+        return self.lib.pupil_support(pupil_d.data_ptr(), pupil_d.shape[0], self.stream())
+
+    def plan(self, pn: int, N: int, support, generic: bool = False) -> _native.Plan:
+        key = (pn, N, tuple(support), bool(generic))
         p = self._plans.get(key)
         if p is None:
-            p = self._plans[key] = self.lib.plan_create(pn, N, bbox)
+            p = self._plans[key] = self.lib.plan_create(pn, N, support, _native.PLAN_GENERIC if generic else 0)
         return p
 
-    def workspace(self, nbytes: int) -> torch.Tensor:
-        if self._workspace is None or self._workspace.numel() < nbytes:
-            self._workspace = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=self.device)
-        return self._workspace
+    def plan_for(self, pn: int, N: int, support, shifts_d: torch.Tensor) -> _native.Plan:
+        """Fast coarse-grid plan when no source point wraps the pupil window, generic plan otherwise."""
+        plan = self.plan(pn, N, support)
+        if plan.path == 2:
+            n = int(shifts_d.shape[0])
+            bounds = self.lib.shift_bounds(shifts_d.data_ptr() if n else None, n, self.stream())
+            if not plan.shifts_fit(bounds):
+                plan = self.plan(pn, N, support, generic=True)
+        return plan
+
+    def workspace(self, nbytes: int, slot: str = "t") -> torch.Tensor:
+        ws = self._workspaces.get(slot)
+        if ws is None or ws.numel() < nbytes:
+            ws = self._workspaces[slot] = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=self.device)
+        return ws
 
     # -- hot path --------------------------------------------------------------------------
     def accumulate(self, plan: _native.Plan, maskFT_d, pupil_d, shifts_d, intensity, weights_d=None, batch: int = 0):
@@ -106,18 +121,25 @@ class AbbeEngine:
     def finalize(self, plan: _native.Plan, intensity: torch.Tensor, eps: float) -> torch.Tensor:
         side = plan.output_side(eps)
         out = torch.empty((side, side), dtype=torch.float32, device=self.device)
-        plan.finalize(intensity.data_ptr(), eps, out.data_ptr(), self.stream())
+        fwb = plan.finalize_workspace_bytes()
+        fws = self.workspace(fwb, "finalize")
+        plan.finalize(intensity.data_ptr(), eps, out.data_ptr(), fws.data_ptr(), fwb, self.stream())
         return out
 
     def unpermute(self, plan: _native.Plan, intensity: torch.Tensor) -> torch.Tensor:
         out = torch.empty((plan.pn, plan.pn), dtype=torch.float32, device=self.device)
-        plan.unpermute(intensity.data_ptr(), out.data_ptr(), self.stream())
+        fwb = plan.finalize_workspace_bytes()
+        fws = self.workspace(fwb, "finalize")
+        plan.unpermute(intensity.data_ptr(), out.data_ptr(), fws.data_ptr(), fwb, self.stream())
         return out
 
     def abbe_fft(self, maskFT, pupilF, lightsource, pixelSize, deltaK, wavelength, *, weights=None, batch: int = 0,
-                 shifts=None, reduce_fn=None, postprocess: bool = True) -> torch.Tensor:
+                 shifts=None, reduce_fn=None, postprocess: bool = True, generic: bool = False,
+                 plan: _native.Plan | None = None) -> torch.Tensor:
         """abbeImage(fft=True).  `shifts` (int32 [n,2]) overrides the source-point extraction and
-        `reduce_fn(intensity)` runs between accumulation and post-processing (multi-GPU sum)."""
+        `reduce_fn(intensity)` runs between accumulation and post-processing (multi-GPU sum).
+        `generic` forces the fine-grid kernels; `plan` pins a plan chosen by the caller (all ranks of a
+        sharded image must use the same one so that their intensity planes can be summed)."""
         dev = self.device
         with torch.cuda.device(dev):
             maskFT_d = _as_c64(maskFT, dev)
@@ -130,7 +152,9 @@ class AbbeEngine:
             else:
                 shifts_d = shifts.to(device=dev, dtype=torch.int32).contiguous()
             w_d = None if weights is None else weights.to(device=dev, dtype=torch.float32).contiguous()
-            plan = self.plan(pn, N, self.pupil_bbox(pupil_d))
+            if plan is None:
+                support = self.pupil_support(pupil_d)
+                plan = self.plan(pn, N, support, generic=True) if generic else self.plan_for(pn, N, support, shifts_d)
             intensity = self.intensity_plane(plan)
             self.accumulate(plan, maskFT_d, pupil_d, shifts_d, intensity, w_d, batch)
             if reduce_fn is not None:
@@ -143,7 +167,7 @@ class AbbeEngine:
             pf_d = _as_c64(pf, dev)
             maskFT_d = _as_c64(maskFT, dev)
             pn = maskFT_d.shape[0]
-            plan = self.plan(pn, int(N), self.pupil_bbox(pf_d))
+            plan = self.plan(pn, int(N), self.pupil_bbox(pf_d), generic=True)
             wsb = plan.workspace_bytes(1)
             ws = self.workspace(wsb)
             field = torch.empty((pn, pn), dtype=torch.complex64, device=dev)

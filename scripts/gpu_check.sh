@@ -13,7 +13,7 @@ echo "bench exit $?" >> gpurun_out/${TAG}_bench.log
 if [ "${SKIP_NCU:-0}" != "1" ]; then
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 400 --csv \
     --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/${TAG}_ncu_launch.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:abbe_ -s 8 -c 4 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:abbe_fast -s 8 -c 4 \
     -o gpurun_out/${TAG}_prof python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/${TAG}_ncu_full.log 2>&1
 fi
 tail -5 gpurun_out/${TAG}_gpu_tests.log; cat gpurun_out/${TAG}_smoke.log | tail -2; tail -c 3000 gpurun_out/${TAG}_bench.log

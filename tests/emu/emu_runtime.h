@@ -47,23 +47,27 @@ inline void fiber_yield() {
 }
 
 struct EmuCtx {
-    int tid_, bdim_, bx_, by_, bz_;
+    int tid_, bdim_, bx_, by_, bz_, gdx_;
     int tid() const { return tid_; }
     int bdim() const { return bdim_; }
     int bx() const { return bx_; }
     int by() const { return by_; }
     int bz() const { return bz_; }
+    int gdx() const { return gdx_; }
     void sync() const { fiber_yield(); }
+    // a warp barrier is emulated by the (stronger) CTA-wide phase boundary; every thread of the CTA
+    // executes the same number of them in the kernels that use it
+    void sync_warp() const { fiber_yield(); }
 };
 
 // run one CTA of `nthreads` fibers; body(ctx) is the kernel body bound to its parameters
 template <class Body>
-void run_cta(int nthreads, int bx, int by, int bz, Body body) {
+void run_cta(int nthreads, int bx, int by, int bz, int gdx, Body body) {
     static const size_t STACK = 256 * 1024;
     Sched s;
     s.fibers.resize(nthreads);
     s.body = [&](int tid) {
-        EmuCtx ctx{tid, nthreads, bx, by, bz};
+        EmuCtx ctx{tid, nthreads, bx, by, bz, gdx};
         body(ctx);
     };
     cur_sched() = &s;
@@ -97,7 +101,7 @@ void launch(int gx, int gy, int gz, int nthreads, size_t smem_bytes, Body body) 
         for (int y = 0; y < gy; ++y)
             for (int x = 0; x < gx; ++x) {
                 memset(smem.data(), 0xCD, smem.size());  // poison: uninitialised reads show up as garbage
-                run_cta(nthreads, x, y, z, [&](const EmuCtx& ctx) { body(ctx, smem.data()); });
+                run_cta(nthreads, x, y, z, gx, [&](const EmuCtx& ctx) { body(ctx, smem.data()); });
             }
 }
 

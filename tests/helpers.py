@@ -49,32 +49,38 @@ def _ptr(a):
 
 
 def emu_abbe_fft(maskFT, pupil, lightsource, pixel_size, wavelength, batch=0, weights=None, postprocess=True,
-                 shifts=None):
+                 shifts=None, force_generic=False):
     """abbeImage(fft=True) through the C ABI on the CPU emulation (numpy buffers)."""
     lib = emu_lib()
     pn = maskFT.shape[0]
     eps, N = lib.epsilon_n(4 / pn, pixel_size, wavelength)
     maskFT = np.ascontiguousarray(maskFT, dtype=np.complex64)
     pupil = np.ascontiguousarray(pupil, dtype=np.complex64)
-    bbox = lib.pupil_bbox(_ptr(pupil), pn)
-    plan = lib.plan_create(pn, N, bbox)
+    support = lib.pupil_support(_ptr(pupil), pn)
     if shifts is None:
         shifts = O.source_shifts(lightsource, pn)
     shifts = np.ascontiguousarray(shifts, dtype=np.int32)
     n_src = shifts.shape[0]
+    plan = lib.plan_create(pn, N, support)
+    bounds = lib.shift_bounds(_ptr(shifts) if n_src else None, n_src)
+    if force_generic or (plan.path == 2 and not plan.shifts_fit(bounds)):
+        plan.close()
+        plan = lib.plan_create(pn, N, support, _native.PLAN_GENERIC)
     inten = np.zeros(plan.intensity_elems, dtype=np.float32)
     wsb = plan.workspace_bytes(batch)
     ws = np.zeros(max(wsb, 8), dtype=np.uint8)
     w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float32)
     plan.accumulate(_ptr(maskFT), _ptr(pupil), _ptr(shifts) if n_src else None, None if w is None else _ptr(w),
                     n_src, batch, _ptr(inten), _ptr(ws), wsb)
+    fwb = plan.finalize_workspace_bytes()
+    fws = np.zeros(max(fwb, 8), dtype=np.uint8)
     if postprocess:
         side = plan.output_side(eps)
         out = np.zeros((side, side), dtype=np.float32)
-        plan.finalize(_ptr(inten), eps, _ptr(out))
+        plan.finalize(_ptr(inten), eps, _ptr(out), _ptr(fws), fwb)
     else:
         out = np.zeros((pn, pn), dtype=np.float32)
-        plan.unpermute(_ptr(inten), _ptr(out))
-    info = dict(N=N, eps=eps, M=plan.M, R=plan.R, bbox=bbox, n_src=n_src)
+        plan.unpermute(_ptr(inten), _ptr(out), _ptr(fws), fwb)
+    info = dict(N=N, eps=eps, M=plan.M, R=plan.R, path=plan.path, support=support, n_src=n_src, bounds=bounds)
     plan.close()
     return out, info

@@ -37,6 +37,45 @@ def test_emu_batching_weights_and_empty_source():
     assert z.shape == (64, 64) and not z.any()
 
 
+@pytest.mark.parametrize("pn,ps,win", [(128, 25, 33), (128, 12, 33), (64, 25, 30), (128, 25, 65)])
+def test_emu_fast_path_dense_window(pn, ps, win):
+    """Fast coarse-grid path on a dense random window.  win = M+1 makes the rim rows/columns fully
+    populated, so the aliased +-M frequency line carries real energy and the rim sums must be right;
+    win < M+1 exercises the no-rim branch.  Checked against the oracle and the generic path."""
+    rng = np.random.default_rng(pn + win)
+    lo = pn // 2 - win // 2
+    pup = np.zeros((pn, pn), np.complex64)
+    pup[lo:lo + win, lo:lo + win] = rng.standard_normal((win, win)) + 1j * rng.standard_normal((win, win))
+    mft = (rng.standard_normal((pn, pn)) + 1j * rng.standard_normal((pn, pn))).astype(np.complex64)
+    shifts = np.array([[0, 0], [5, -7], [-lo, lo - 1 + (pn - 2 * lo - win + 1)], [3, 3]], np.int32)
+    shifts[2] = [-lo, pn - (lo + win)]  # extreme corner of the no-wrap range
+    w = np.array([1.0, 2.0, 0.5, 1.5], np.float32)
+    fast, info = H.emu_abbe_fft(mft, pup, None, float(ps), 193.0, shifts=shifts, weights=w, postprocess=False, batch=3)
+    assert info["path"] == 2, info
+    _, N = O.calculate_epsilon_n(4 / pn, ps, 193.0)
+    ref = np.zeros((pn, pn))
+    for (d0, d1), wi in zip(shifts, w):
+        ref += wi * np.abs(O.calculate_fft_aerial(np.roll(pup, (d0, d1), (0, 1)), mft, pn, N)) ** 2
+    assert O.rel_l2(fast, ref) < H.TOL
+    gen, info2 = H.emu_abbe_fft(mft, pup, None, float(ps), 193.0, shifts=shifts, weights=w, postprocess=False,
+                                force_generic=True)
+    assert info2["path"] == 1
+    assert O.rel_l2(fast, gen) < H.TOL
+
+
+def test_emu_fast_path_subfft_256():
+    """pn = 512 -> sub-FFT 256 = radix 32 x 8 (two passes with a partial second radix)."""
+    c_pn = 512
+    pf, _ = O.pupil_function([0, 0, 0.01, 0, 60, 0.01], c_pn, 0.7, 193.0)
+    rng = np.random.default_rng(1)
+    mft = (rng.standard_normal((c_pn, c_pn)) + 1j * rng.standard_normal((c_pn, c_pn))).astype(np.complex64)
+    shifts = np.array([[10, -20]], np.int32)
+    img, info = H.emu_abbe_fft(mft, pf, None, 25.0, 193.0, shifts=shifts, postprocess=False)
+    assert info["path"] == 2 and info["M"] == 256, info
+    e = O.calculate_fft_aerial(np.roll(pf, (10, -20), (0, 1)), mft, c_pn, 1024)
+    assert O.rel_l2(img, np.abs(e) ** 2) < H.TOL
+
+
 def test_emu_complex_field():
     f = KAT["field_fft_64"]
     lib = H.emu_lib()
