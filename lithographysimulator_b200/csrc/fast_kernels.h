@@ -131,21 +131,50 @@ LITHO_HD void fast_rows_body(const FastRowsParams& P, const Ctx& ctx, cplx* smem
             const int mr = iclamp(P.pr0 + line + sh.x, 0, P.pn - 1);
             const int mc = iclamp(P.pc0 + sh.y, 0, P.pn - P.Sc);
             const cplx* mrow = P.mask + (size_t)mr * P.pn + mc;
+            // Branch-free loads (index clamped, value masked afterwards) so that all loads of a half are
+            // in flight together instead of one load-use round trip per element.
+            const int last = P.Sc - 1;
+            const cplx* pg = prow + g;
+            const cplx* mg = mrow + g;
+            if (last >= M - 1) {  // common case: every slot has an input
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-                const int u = g + TG * e;
-                cplx x = mk(0.f, 0.f);
-                if (u < P.Sc) {
-                    x = cmul(ldg_c(prow + u), ldg_c(mrow + u));
-                    if (r) x = cmul(x, tab[F::PRE_OFF + u]);
+                for (int h = 0; h < 2; ++h) {
+                    cplx a[16], b[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        a[i] = ldg_c(pg + TG * (16 * h + i));
+                        b[i] = ldg_c(mg + TG * (16 * h + i));
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[16 * h + i] = cmul(a[i], b[i]);
                 }
-                if (e == 0) {
-                    if (g == 0 && P.Sc > M) {  // rim input u = M folds onto slot 0 with w_2M^(r*M) = (-1)^r
-                        const cplx y = cmul(ldg_c(prow + M), ldg_c(mrow + M));
-                        x = r ? csub(x, y) : cadd(x, y);
+            } else {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    cplx a[16], b[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int u = g + TG * (16 * h + i);
+                        const int uc = u < last ? u : last;
+                        a[i] = ldg_c(prow + uc);
+                        b[i] = ldg_c(mrow + uc);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int u = g + TG * (16 * h + i);
+                        const cplx x = cmul(a[i], b[i]);
+                        v[16 * h + i] = mk(u <= last ? x.x : 0.f, u <= last ? x.y : 0.f);
                     }
                 }
-                v[e] = x;
+            }
+            if (r) {
+#pragma unroll
+                for (int e = 0; e < 32; ++e) v[e] = cmul(v[e], tab[F::PRE_OFF + g + TG * e]);
+            }
+            if (P.Sc > M) {  // rim input u = M folds onto slot 0 with w_2M^(r*M) = (-1)^r
+                const cplx y = cmul(ldg_c(prow + M), ldg_c(mrow + M));
+                const float sgn = (g == 0) ? (r ? -1.f : 1.f) : 0.f;
+                v[0] = mk(v[0].x + sgn * y.x, v[0].y + sgn * y.y);
             }
         } else {
 #pragma unroll
@@ -185,21 +214,30 @@ LITHO_HD void fast_cols_body(const FastColsParams& P, const Ctx& ctx, cplx* smem
     for (int sl = 0; sl < P.batch; ++sl) {
         const cplx* src = P.T + ((size_t)(sl * 2 + rc) * P.Sr) * M + kc;
         cplx v[32];
+        const int last = P.Sr - 1;
+        const cplx* srcg = src + (size_t)g * M;
+        // Branch-free loads so that all 32 are in flight together (one load-use round trip per FFT,
+        // not per element).  Common case Sr >= M: every slot has an input and no masking is needed.
+        if (last >= M - 1) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-            const int u = g + TG * e;
-            cplx x = mk(0.f, 0.f);
-            if (u < P.Sr) {
-                x = ldg_c(src + (size_t)u * M);
-                if (rr) x = cmul(x, tab[F::PRE_OFF + u]);
+            for (int e = 0; e < 32; ++e) v[e] = ldg_c(srcg + (size_t)e * (TG * M));
+        } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+                const int u = g + TG * e;
+                const cplx* pa = (u <= last) ? srcg + (size_t)e * (TG * M) : src + (size_t)last * M;
+                const cplx x = ldg_c(pa);
+                v[e] = mk(u <= last ? x.x : 0.f, u <= last ? x.y : 0.f);
             }
-            if (e == 0) {
-                if (g == 0 && P.Sr > M) {
-                    const cplx y = ldg_c(src + (size_t)M * M);
-                    x = rr ? csub(x, y) : cadd(x, y);
-                }
-            }
-            v[e] = x;
+        }
+        if (rr) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = cmul(v[e], tab[F::PRE_OFF + g + TG * e]);
+        }
+        if (P.Sr > M) {
+            const cplx y = ldg_c(src + (size_t)M * M);
+            const float sgn = (g == 0) ? (rr ? -1.f : 1.f) : 0.f;
+            v[0] = mk(v[0].x + sgn * y.x, v[0].y + sgn * y.y);
         }
         fft_run<M, 32, false>(v, ex, CB, g, tw, gs);
         const float w = P.weights ? P.weights[P.s_begin + sl] : 1.f;
