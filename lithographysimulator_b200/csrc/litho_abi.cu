@@ -276,6 +276,10 @@ struct litho_plan {
     int ext[8];      // non-zero extents of the first/last window row and column (window coordinates)
     cplx* tables;    // device twiddle tables of the fast kernels (owned by the plan)
     int n_sm;
+#if !defined(LITHO_EMU)
+    cudaStream_t aux_stream;  // row passes of the fast path run here, overlapping the column passes
+    cudaEvent_t ev_start, ev_rows[2], ev_cols[2];
+#endif
 };
 
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
@@ -505,6 +509,9 @@ int litho_plan_create_ex(int pn, int N, const int* bbox, int flags, litho_plan_t
     size_t per = (size_t)p->zp.R * p->Sr * p->zp.Wr * sizeof(cplx);
     // ---- fast path eligibility: even window fit S <= Mf+1, coarse grid Nc = 2*Mf no finer than N ----
     p->path = 1; p->tables = nullptr; p->Mf = p->Nc = p->q = 0; p->rim_row = p->rim_col = 0;
+#if !defined(LITHO_EMU)
+    p->aux_stream = nullptr;
+#endif
     p->n_sm = 148;
 #if !defined(LITHO_EMU)
     {
@@ -532,6 +539,21 @@ int litho_plan_create_ex(int pn, int N, const int* bbox, int flags, litho_plan_t
             delete p;
             return fail(LITHO_ERR_CUDA, std::string("plan_create: fast tables: ") + be_errstr(rc));
         }
+#if !defined(LITHO_EMU)
+        {
+            cudaError_t e = cudaStreamCreateWithFlags(&p->aux_stream, cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming);
+            for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+                e = cudaEventCreateWithFlags(&p->ev_rows[i], cudaEventDisableTiming);
+                if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_cols[i], cudaEventDisableTiming);
+            }
+            if (e != cudaSuccess) {
+                be_free(p->tables);
+                delete p;
+                return fail(LITHO_ERR_CUDA, std::string("plan_create: stream/event: ") + cudaGetErrorString(e));
+            }
+        }
+#endif
         p->path = 2; p->Mf = Mf; p->Nc = 2 * Mf; p->q = N / (2 * Mf);
         p->rim_row = (p->Sr == Mf + 1);
         p->rim_col = (p->Sc == Mf + 1);
@@ -554,6 +576,17 @@ int litho_plan_create_ex(int pn, int N, const int* bbox, int flags, litho_plan_t
 void litho_plan_destroy(litho_plan_t* p) {
     if (!p) return;
     if (p->tables) be_free(p->tables);
+#if !defined(LITHO_EMU)
+    if (p->aux_stream) {
+        cudaStreamSynchronize(p->aux_stream);
+        cudaStreamDestroy(p->aux_stream);
+        cudaEventDestroy(p->ev_start);
+        for (int i = 0; i < 2; ++i) {
+            cudaEventDestroy(p->ev_rows[i]);
+            cudaEventDestroy(p->ev_cols[i]);
+        }
+    }
+#endif
     delete p;  // the w_L twiddle table belongs to the process-wide cache
 }
 
@@ -596,7 +629,7 @@ size_t litho_plan_workspace_bytes(const litho_plan_t* p, int batch) {
     if (!p) return 0;
     if (batch <= 0) batch = p->default_batch;
     if (p->path == 2) {
-        const size_t fast = (size_t)batch * 2 * p->Sr * p->Mf * sizeof(cplx);
+        const size_t fast = (size_t)2 * batch * 2 * p->Sr * p->Mf * sizeof(cplx);  // two T slots (double buffer)
         const size_t gen1 = generic_t_bytes(p, 1);
         return fast > gen1 ? fast : gen1;
     }
@@ -681,10 +714,38 @@ int litho_abbe_fft_accumulate_ex(const litho_plan_t* p, const void* maskFT, cons
         memset(&fc, 0, sizeof(fc));
         fc.T = (const cplx*)workspace; fc.Sr = p->Sr; fc.weights = weights; fc.tables = p->tables;
         fc.ic = intensity;
-        for (int s0 = 0; s0 < n_src; s0 += batch) {
+        // T is double-buffered: the row pass of batch b+1 runs on the plan's auxiliary stream while the
+        // column pass of batch b runs on the caller's stream, so the tail of one kernel overlaps the head
+        // of the other (both are short, ~20-40 us at cfg3).  rows(b) -> cols(b) and cols(b) -> rows(b+2)
+        // (slot reuse) are ordered with events; all column passes stay on one stream, which also
+        // serialises their read-modify-write of the intensity plane.
+        const size_t slot_elems = (size_t)batch * 2 * p->Sr * p->Mf;
+        cplx* Tslot[2] = {(cplx*)workspace, (cplx*)workspace + slot_elems};
+#if !defined(LITHO_EMU)
+        const bool overlap = (phases == 3) && p->aux_stream != nullptr;
+        if (overlap) {
+            BE_CHECK((int)cudaEventRecord(p->ev_start, st));
+            BE_CHECK((int)cudaStreamWaitEvent(p->aux_stream, p->ev_start, 0));
+        }
+#else
+        const bool overlap = false;
+#endif
+        int b = 0;
+        for (int s0 = 0; s0 < n_src; s0 += batch, ++b) {
             const int nb = (n_src - s0) < batch ? (n_src - s0) : batch;
-            fr.s_begin = s0; fr.batch = nb;
-            fc.s_begin = s0; fc.batch = nb;
+            fr.s_begin = s0; fr.batch = nb; fr.T = Tslot[b & 1];
+            fc.s_begin = s0; fc.batch = nb; fc.T = Tslot[b & 1];
+#if !defined(LITHO_EMU)
+            if (overlap) {
+                if (b >= 2) BE_CHECK((int)cudaStreamWaitEvent(p->aux_stream, p->ev_cols[b & 1], 0));
+                BE_CHECK(dispatch_fast_rows(p->Mf, fr, p->n_sm * 2, p->aux_stream));
+                BE_CHECK((int)cudaEventRecord(p->ev_rows[b & 1], p->aux_stream));
+                BE_CHECK((int)cudaStreamWaitEvent(st, p->ev_rows[b & 1], 0));
+                BE_CHECK(dispatch_fast_cols(p->Mf, fc, st));
+                BE_CHECK((int)cudaEventRecord(p->ev_cols[b & 1], st));
+                continue;
+            }
+#endif
             if (phases & 1) BE_CHECK(dispatch_fast_rows(p->Mf, fr, p->n_sm * 2, st));
             if (phases & 2) BE_CHECK(dispatch_fast_cols(p->Mf, fc, st));
         }
