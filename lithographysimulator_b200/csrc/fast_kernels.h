@@ -17,7 +17,9 @@
 //     per image (litho_abi.cu: finalize).  The single aliased frequency line |d| = M, which exists
 //     only when S = M+1 (the pupil's fp16 rim pixels), is carried separately by rim_body below.
 //
-// FFTs use 32 points per thread (radix 32 x 32 for M = 1024): one shared-memory exchange per FFT.
+// FFTs hold PPT = 32 points per thread (radix 32 x 32 for M = 1024: one shared-memory exchange, 128
+// registers) or PPT = 16 (radix 16 x 16 x 4: two exchanges, 64 registers, twice the resident warps);
+// the plan picks the variant per M from measurements.
 #pragma once
 #include "fft_core.h"
 
@@ -25,49 +27,55 @@ namespace litho {
 
 LITHO_HD int iclamp(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
-template <int M>
+template <int M, int PPT>
 struct FastShape {
-    using Sh = FftShape<M, 32>;
+    using Sh = FftShape<M, PPT>;
     static constexpr int TG = Sh::TG;
     static constexpr int R1 = Sh::NP > 1 ? Sh::radix(1) : 1;
     static constexpr int R2 = Sh::NP > 2 ? Sh::radix(2) : 1;
-    static constexpr int NS1 = 32, NS2 = 32 * R1;
+    static constexpr int NS1 = PPT, NS2 = PPT * R1;
     // shared-memory twiddle tables: pre[u] = w_2M^u (u = 0..M), tw1[(t-1)*NS1+k], tw2[(t-1)*NS2+k]
     static constexpr int PRE_OFF = 0;
     static constexpr int TW1_OFF = M + 1;
     static constexpr int TW2_OFF = TW1_OFF + (R1 - 1) * NS1;
     static constexpr int NTAB = TW2_OFF + (R2 - 1) * NS2;
     static constexpr int NTAB_PAD = (NTAB + 1) & ~1;  // keep the exchange region 16-byte aligned
-    // rows kernel: one FFT group per TG threads
-    static constexpr bool WARP_GROUP = (TG <= 32);
-    static constexpr int ROW_THREADS = WARP_GROUP ? 256 : TG;
+    // rows kernel: one FFT group per TG threads; groups inside a warp sync with __syncwarp, groups of
+    // 2..4 warps with a named barrier, a group that is the whole CTA with __syncthreads
+    static constexpr int ROW_THREADS = TG <= 256 ? 256 : TG;
     static constexpr int ROW_GROUPS = ROW_THREADS / TG;
+    static constexpr int ROW_SYNC = TG <= 32 ? 0 : (ROW_GROUPS > 1 ? 1 : 2);  // 0 warp, 1 named barrier, 2 CTA
     static constexpr size_t ROW_SMEM = (size_t)(NTAB_PAD + ROW_GROUPS * Sh::SMEM_ELEMS) * sizeof(cplx);
-    // cols kernel: CB adjacent columns per CTA, column fastest in the thread index
-    static constexpr int CB = (M <= 512) ? 16 : (M == 1024 ? 8 : 4);
+    // cols kernel: CB adjacent columns per CTA, column fastest in the thread index (256 threads per CTA
+    // where possible; CB >= 4 keeps every global request at full 32-byte sectors)
+    static constexpr int CB = (256 / TG) >= 16 ? 16 : ((256 / TG) >= 4 ? (256 / TG) : 4);
     static constexpr int COL_THREADS = CB * TG;
     static constexpr size_t COL_SMEM = (size_t)(NTAB_PAD + CB * Sh::SMEM_ELEMS) * sizeof(cplx);
-    // occupancy targets: 128 registers per thread, i.e. 512 resident threads per SM
-    static constexpr int COL_MIN_BLOCKS = (512 / COL_THREADS) >= 1 ? (512 / COL_THREADS) : 1;
-    static constexpr int ROW_MIN_BLOCKS = (512 / ROW_THREADS) >= 1 ? (512 / ROW_THREADS) : 1;
+    // occupancy targets: 4 registers per FFT point held -> 128 regs (PPT 32) / 64 regs (PPT 16) per thread
+    static constexpr int TARGET_THREADS = PPT == 32 ? 512 : 1024;
+    static constexpr int COL_MIN_BLOCKS = (TARGET_THREADS / COL_THREADS) >= 1 ? (TARGET_THREADS / COL_THREADS) : 1;
+    static constexpr int ROW_MIN_BLOCKS = (TARGET_THREADS / ROW_THREADS) >= 1 ? (TARGET_THREADS / ROW_THREADS) : 1;
 };
 
-template <int M>
+template <int M, int PPT>
 struct SmemTw {
     const cplx* tab;
     template <int PASS>
     LITHO_HD cplx get(int t, int k) const {
-        using F = FastShape<M>;
+        using F = FastShape<M, PPT>;
         if constexpr (PASS == 1) return tab[F::TW1_OFF + (t - 1) * F::NS1 + k];
         else return tab[F::TW2_OFF + (t - 1) * F::NS2 + k];
     }
 };
 
-template <class Ctx, bool WARP>
+// MODE 0: warp barrier, 1: named barrier `id` over `n` threads, 2: CTA barrier
+template <class Ctx, int MODE>
 struct GroupSync {
     const Ctx& ctx;
+    int id, n;
     LITHO_HD void sync() const {
-        if constexpr (WARP) ctx.sync_warp();
+        if constexpr (MODE == 0) ctx.sync_warp();
+        else if constexpr (MODE == 1) ctx.sync_named(id, n);
         else ctx.sync();
     }
 };
@@ -92,28 +100,29 @@ struct FastColsParams {
     float* ic;  // [2][2][M][M] : ((rr*2 + rc)*M + kr)*M + kc, accumulated
 };
 
-template <int M, class Ctx>
+template <int M, int PPT, class Ctx>
 LITHO_HD void fast_load_tables(const cplx* tables, cplx* tab, const Ctx& ctx) {
-    for (int i = ctx.tid(); i < FastShape<M>::NTAB; i += ctx.bdim()) tab[i] = tables[i];
+    for (int i = ctx.tid(); i < FastShape<M, PPT>::NTAB; i += ctx.bdim()) tab[i] = tables[i];
     ctx.sync();
 }
 
 // grid.x = any (persistent over the batch*Sr*2 work items), block = ROW_THREADS
-template <int M, class Ctx>
+template <int M, int PPT, class Ctx>
 LITHO_HD void fast_rows_body(const FastRowsParams& P, const Ctx& ctx, cplx* smem) {
-    using F = FastShape<M>;
+    using F = FastShape<M, PPT>;
     using Sh = typename F::Sh;
     constexpr int TG = F::TG;
+    constexpr int H = PPT / 2;
     cplx* tab = smem;
-    fast_load_tables<M>(P.tables, tab, ctx);
+    fast_load_tables<M, PPT>(P.tables, tab, ctx);
     const int grp = ctx.tid() / TG;
     const int g = ctx.tid() - grp * TG;
     cplx* ex = smem + F::NTAB_PAD + grp * Sh::SMEM_ELEMS;
     const int total = P.batch * P.Sr * 2;
     const int stride = ctx.gdx() * F::ROW_GROUPS;
     const int rounds = (total + stride - 1) / stride;
-    const SmemTw<M> tw{tab};
-    const GroupSync<Ctx, F::WARP_GROUP> gs{ctx};
+    const SmemTw<M, PPT> tw{tab};
+    const GroupSync<Ctx, F::ROW_SYNC> gs{ctx, 1 + grp, TG};
 
     for (int it = 0; it < rounds; ++it) {
         const int item = it * stride + ctx.bx() * F::ROW_GROUPS + grp;
@@ -122,7 +131,7 @@ LITHO_HD void fast_rows_body(const FastRowsParams& P, const Ctx& ctx, cplx* smem
         const int li = item >> 1;
         const int sl = active ? li / P.Sr : 0;
         const int line = active ? li - sl * P.Sr : 0;
-        cplx v[32];
+        cplx v[PPT];
         if (active) {
             const int2_ sh = P.shifts[P.s_begin + sl];
             const cplx* prow = P.pupil + (size_t)(P.pr0 + line) * P.pn + P.pc0;
@@ -139,37 +148,37 @@ LITHO_HD void fast_rows_body(const FastRowsParams& P, const Ctx& ctx, cplx* smem
             if (last >= M - 1) {  // common case: every slot has an input
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    cplx a[16], b[16];
+                    cplx a[H], b[H];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        a[i] = ldg_c(pg + TG * (16 * h + i));
-                        b[i] = ldg_c(mg + TG * (16 * h + i));
+                    for (int i = 0; i < H; ++i) {
+                        a[i] = ldg_c(pg + TG * (H * h + i));
+                        b[i] = ldg_c(mg + TG * (H * h + i));
                     }
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[16 * h + i] = cmul(a[i], b[i]);
+                    for (int i = 0; i < H; ++i) v[H * h + i] = cmul(a[i], b[i]);
                 }
             } else {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    cplx a[16], b[16];
+                    cplx a[H], b[H];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int u = g + TG * (16 * h + i);
+                    for (int i = 0; i < H; ++i) {
+                        const int u = g + TG * (H * h + i);
                         const int uc = u < last ? u : last;
                         a[i] = ldg_c(prow + uc);
                         b[i] = ldg_c(mrow + uc);
                     }
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int u = g + TG * (16 * h + i);
+                    for (int i = 0; i < H; ++i) {
+                        const int u = g + TG * (H * h + i);
                         const cplx x = cmul(a[i], b[i]);
-                        v[16 * h + i] = mk(u <= last ? x.x : 0.f, u <= last ? x.y : 0.f);
+                        v[H * h + i] = mk(u <= last ? x.x : 0.f, u <= last ? x.y : 0.f);
                     }
                 }
             }
             if (r) {
 #pragma unroll
-                for (int e = 0; e < 32; ++e) v[e] = cmul(v[e], tab[F::PRE_OFF + g + TG * e]);
+                for (int e = 0; e < PPT; ++e) v[e] = cmul(v[e], tab[F::PRE_OFF + g + TG * e]);
             }
             if (P.Sc > M) {  // rim input u = M folds onto slot 0 with w_2M^(r*M) = (-1)^r
                 const cplx y = cmul(ldg_c(prow + M), ldg_c(mrow + M));
@@ -178,25 +187,25 @@ LITHO_HD void fast_rows_body(const FastRowsParams& P, const Ctx& ctx, cplx* smem
             }
         } else {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] = mk(0.f, 0.f);
+            for (int e = 0; e < PPT; ++e) v[e] = mk(0.f, 0.f);
         }
-        fft_run<M, 32, false>(v, ex, 1, g, tw, gs);
+        fft_run<M, PPT, false>(v, ex, 1, g, tw, gs);
         if (active) {
             cplx* dst = P.T + ((size_t)(sl * 2 + r) * P.Sr + line) * M + g;
 #pragma unroll
-            for (int e = 0; e < 32; ++e) dst[TG * e] = v[e];
+            for (int e = 0; e < PPT; ++e) dst[TG * e] = v[e];
         }
     }
 }
 
 // grid.x = 2*M/CB column blocks (rc major), grid.y = 2 (rr), block = COL_THREADS
-template <int M, class Ctx>
+template <int M, int PPT, class Ctx>
 LITHO_HD void fast_cols_body(const FastColsParams& P, const Ctx& ctx, cplx* smem) {
-    using F = FastShape<M>;
+    using F = FastShape<M, PPT>;
     constexpr int TG = F::TG;
     constexpr int CB = F::CB;
     cplx* tab = smem;
-    fast_load_tables<M>(P.tables, tab, ctx);
+    fast_load_tables<M, PPT>(P.tables, tab, ctx);
     const int col = ctx.tid() % CB;
     const int g = ctx.tid() / CB;
     cplx* ex = smem + F::NTAB_PAD + col;
@@ -204,26 +213,26 @@ LITHO_HD void fast_cols_body(const FastColsParams& P, const Ctx& ctx, cplx* smem
     constexpr int NBLK = M / CB;
     const int rc = ctx.bx() / NBLK;
     const int kc = (ctx.bx() - rc * NBLK) * CB + col;
-    const SmemTw<M> tw{tab};
-    const GroupSync<Ctx, false> gs{ctx};
+    const SmemTw<M, PPT> tw{tab};
+    const GroupSync<Ctx, 2> gs{ctx, 0, 0};
 
-    float acc[32];
+    float acc[PPT];
 #pragma unroll
-    for (int e = 0; e < 32; ++e) acc[e] = 0.f;
+    for (int e = 0; e < PPT; ++e) acc[e] = 0.f;
 
     for (int sl = 0; sl < P.batch; ++sl) {
         const cplx* src = P.T + ((size_t)(sl * 2 + rc) * P.Sr) * M + kc;
-        cplx v[32];
+        cplx v[PPT];
         const int last = P.Sr - 1;
         const cplx* srcg = src + (size_t)g * M;
-        // Branch-free loads so that all 32 are in flight together (one load-use round trip per FFT,
-        // not per element).  Common case Sr >= M: every slot has an input and no masking is needed.
+        // Branch-free loads so that all of them are in flight together (one load-use round trip per
+        // FFT, not per element).  Common case Sr >= M: every slot has an input, no masking needed.
         if (last >= M - 1) {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] = ldg_c(srcg + (size_t)e * (TG * M));
+            for (int e = 0; e < PPT; ++e) v[e] = ldg_c(srcg + (size_t)e * (TG * M));
         } else {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
+            for (int e = 0; e < PPT; ++e) {
                 const int u = g + TG * e;
                 const cplx* pa = (u <= last) ? srcg + (size_t)e * (TG * M) : src + (size_t)last * M;
                 const cplx x = ldg_c(pa);
@@ -232,21 +241,21 @@ LITHO_HD void fast_cols_body(const FastColsParams& P, const Ctx& ctx, cplx* smem
         }
         if (rr) {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] = cmul(v[e], tab[F::PRE_OFF + g + TG * e]);
+            for (int e = 0; e < PPT; ++e) v[e] = cmul(v[e], tab[F::PRE_OFF + g + TG * e]);
         }
         if (P.Sr > M) {
             const cplx y = ldg_c(src + (size_t)M * M);
             const float sgn = (g == 0) ? (rr ? -1.f : 1.f) : 0.f;
             v[0] = mk(v[0].x + sgn * y.x, v[0].y + sgn * y.y);
         }
-        fft_run<M, 32, false>(v, ex, CB, g, tw, gs);
+        fft_run<M, PPT, false>(v, ex, CB, g, tw, gs);
         const float w = P.weights ? P.weights[P.s_begin + sl] : 1.f;
 #pragma unroll
-        for (int e = 0; e < 32; ++e) acc[e] += w * cnorm2(v[e]);
+        for (int e = 0; e < PPT; ++e) acc[e] += w * cnorm2(v[e]);
     }
     float* dst = P.ic + ((size_t)(rr * 2 + rc) * M + g) * M + kc;
 #pragma unroll
-    for (int e = 0; e < 32; ++e) dst[(size_t)(TG * e) * M] += acc[e];
+    for (int e = 0; e < PPT; ++e) dst[(size_t)(TG * e) * M] += acc[e];
 }
 
 // ----------------------------------------------------------------------------- rim lines

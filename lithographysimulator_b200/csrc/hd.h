@@ -76,6 +76,10 @@ struct DevCtx {
     __device__ __forceinline__ int gdx() const { return gridDim.x; }
     __device__ __forceinline__ void sync() const { __syncthreads(); }
     __device__ __forceinline__ void sync_warp() const { __syncwarp(); }
+    // named barrier over `n` threads (a multiple of 32); id 0 is __syncthreads' barrier, use 1..15
+    __device__ __forceinline__ void sync_named(int id, int n) const {
+        asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+    }
 };
 #endif
 

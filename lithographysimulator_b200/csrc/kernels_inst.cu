@@ -99,59 +99,64 @@ void shape_m(int* rows_fpc, int* cols_cb) {
 
 #if LITHO_INST_M >= 32 && LITHO_INST_M <= 4096
 #if !defined(LITHO_EMU)
-template <int M>
-__global__ void __launch_bounds__(FastShape<M>::ROW_THREADS, FastShape<M>::ROW_MIN_BLOCKS) abbe_fast_rows_kernel(const __grid_constant__ FastRowsParams P) {
+template <int M, int PPT>
+__global__ void __launch_bounds__(FastShape<M, PPT>::ROW_THREADS, FastShape<M, PPT>::ROW_MIN_BLOCKS)
+abbe_fast_rows_kernel(const __grid_constant__ FastRowsParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    fast_rows_body<M>(P, DevCtx{}, reinterpret_cast<cplx*>(smem_raw));
+    fast_rows_body<M, PPT>(P, DevCtx{}, reinterpret_cast<cplx*>(smem_raw));
 }
-template <int M>
-__global__ void __launch_bounds__(FastShape<M>::COL_THREADS, FastShape<M>::COL_MIN_BLOCKS) abbe_fast_cols_kernel(const __grid_constant__ FastColsParams P) {
+template <int M, int PPT>
+__global__ void __launch_bounds__(FastShape<M, PPT>::COL_THREADS, FastShape<M, PPT>::COL_MIN_BLOCKS)
+abbe_fast_cols_kernel(const __grid_constant__ FastColsParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    fast_cols_body<M>(P, DevCtx{}, reinterpret_cast<cplx*>(smem_raw));
+    fast_cols_body<M, PPT>(P, DevCtx{}, reinterpret_cast<cplx*>(smem_raw));
 }
 #endif
 
-template <int M>
+template <int M, int PPT>
 int launch_fast_rows_m(const FastRowsParams& P, int gx, litho_stream_t st) {
-    using F = FastShape<M>;
+    using F = FastShape<M, PPT>;
 #if defined(LITHO_EMU)
     (void)st;
     litho_emu::launch(gx, 1, 1, F::ROW_THREADS, F::ROW_SMEM,
-                      [&](const litho_emu::EmuCtx& c, char* s) { fast_rows_body<M>(P, c, (cplx*)s); });
+                      [&](const litho_emu::EmuCtx& c, char* s) { fast_rows_body<M, PPT>(P, c, (cplx*)s); });
     return 0;
 #else
-    int e = set_smem(abbe_fast_rows_kernel<M>, F::ROW_SMEM);
+    int e = set_smem(abbe_fast_rows_kernel<M, PPT>, F::ROW_SMEM);
     if (e) return e;
-    abbe_fast_rows_kernel<M><<<dim3(gx, 1, 1), dim3(F::ROW_THREADS, 1, 1), F::ROW_SMEM, st>>>(P);
+    abbe_fast_rows_kernel<M, PPT><<<dim3(gx, 1, 1), dim3(F::ROW_THREADS, 1, 1), F::ROW_SMEM, st>>>(P);
     return (int)cudaGetLastError();
 #endif
 }
 
-template <int M>
+template <int M, int PPT>
 int launch_fast_cols_m(const FastColsParams& P, litho_stream_t st) {
-    using F = FastShape<M>;
+    using F = FastShape<M, PPT>;
     const int gx = 2 * (M / F::CB);
 #if defined(LITHO_EMU)
     (void)st;
     litho_emu::launch(gx, 2, 1, F::COL_THREADS, F::COL_SMEM,
-                      [&](const litho_emu::EmuCtx& c, char* s) { fast_cols_body<M>(P, c, (cplx*)s); });
+                      [&](const litho_emu::EmuCtx& c, char* s) { fast_cols_body<M, PPT>(P, c, (cplx*)s); });
     return 0;
 #else
-    int e = set_smem(abbe_fast_cols_kernel<M>, F::COL_SMEM);
+    int e = set_smem(abbe_fast_cols_kernel<M, PPT>, F::COL_SMEM);
     if (e) return e;
-    abbe_fast_cols_kernel<M><<<dim3(gx, 2, 1), dim3(F::COL_THREADS, 1, 1), F::COL_SMEM, st>>>(P);
+    abbe_fast_cols_kernel<M, PPT><<<dim3(gx, 2, 1), dim3(F::COL_THREADS, 1, 1), F::COL_SMEM, st>>>(P);
     return (int)cudaGetLastError();
 #endif
 }
 
-template <int M>
+template <int M, int PPT>
 int fast_ntab_m() {
-    return FastShape<M>::NTAB;
+    return FastShape<M, PPT>::NTAB;
 }
 
-template int launch_fast_rows_m<LITHO_INST_M>(const FastRowsParams&, int, litho_stream_t);
-template int launch_fast_cols_m<LITHO_INST_M>(const FastColsParams&, litho_stream_t);
-template int fast_ntab_m<LITHO_INST_M>();
+template int launch_fast_rows_m<LITHO_INST_M, 32>(const FastRowsParams&, int, litho_stream_t);
+template int launch_fast_cols_m<LITHO_INST_M, 32>(const FastColsParams&, litho_stream_t);
+template int fast_ntab_m<LITHO_INST_M, 32>();
+template int launch_fast_rows_m<LITHO_INST_M, 16>(const FastRowsParams&, int, litho_stream_t);
+template int launch_fast_cols_m<LITHO_INST_M, 16>(const FastColsParams&, litho_stream_t);
+template int fast_ntab_m<LITHO_INST_M, 16>();
 #endif
 
 template int launch_rows_m<LITHO_INST_M>(int, const RowsParams&, int, int, litho_stream_t);

@@ -28,11 +28,11 @@ void shape_m(int* rows_fpc, int* cols_cb);
 // ---- fast path (fast_kernels.h), instantiated for 32 <= M <= 4096 ----
 #include "fast_kernels.h"
 namespace litho {
-template <int M>
+template <int M, int PPT>
 int launch_fast_rows_m(const FastRowsParams& P, int gx, litho_stream_t st);
-template <int M>
+template <int M, int PPT>
 int launch_fast_cols_m(const FastColsParams& P, litho_stream_t st);
-template <int M>
+template <int M, int PPT>
 int fast_ntab_m();
 #define LITHO_FOR_EACH_FAST_M(X) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096)
 }  // namespace litho

@@ -271,7 +271,7 @@ struct litho_plan {
     int default_batch;
     // fast path (fast_kernels.h): coarse grid Nc = 2*Mf, q = N/Nc
     int path;        // 1 = generic fine grid, 2 = fast coarse grid
-    int Mf, Nc, q;
+    int Mf, Nc, q, ppt;
     int rim_row, rim_col;  // Sr == Mf+1 / Sc == Mf+1: the +-Mf frequency line needs the rim sums
     int ext[8];      // non-zero extents of the first/last window row and column (window coordinates)
     cplx* tables;    // device twiddle tables of the fast kernels (owned by the plan)
@@ -284,38 +284,39 @@ struct litho_plan {
 
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
-static int dispatch_fast_rows(int M, const FastRowsParams& P, int gx, litho_stream_t st) {
+static int dispatch_fast_rows(int M, int ppt, const FastRowsParams& P, int gx, litho_stream_t st) {
     switch (M) {
-#define X(m) case m: return launch_fast_rows_m<m>(P, gx, st);
+#define X(m) case m: return ppt == 16 ? launch_fast_rows_m<m, 16>(P, gx, st) : launch_fast_rows_m<m, 32>(P, gx, st);
         LITHO_FOR_EACH_FAST_M(X)
 #undef X
     }
     return -1;
 }
-static int dispatch_fast_cols(int M, const FastColsParams& P, litho_stream_t st) {
+static int dispatch_fast_cols(int M, int ppt, const FastColsParams& P, litho_stream_t st) {
     switch (M) {
-#define X(m) case m: return launch_fast_cols_m<m>(P, st);
+#define X(m) case m: return ppt == 16 ? launch_fast_cols_m<m, 16>(P, st) : launch_fast_cols_m<m, 32>(P, st);
         LITHO_FOR_EACH_FAST_M(X)
 #undef X
     }
     return -1;
 }
-static int dispatch_fast_ntab(int M) {
+static int dispatch_fast_ntab(int M, int ppt) {
     switch (M) {
-#define X(m) case m: return fast_ntab_m<m>();
+#define X(m) case m: return ppt == 16 ? fast_ntab_m<m, 16>() : fast_ntab_m<m, 32>();
         LITHO_FOR_EACH_FAST_M(X)
 #undef X
     }
     return -1;
 }
 
-// host mirror of FastShape<M>: table layout {pre[0..M], tw1[(t-1)*32+k], tw2[(t-1)*NS2+k]}
-static std::vector<cplx> build_fast_tables(int M) {
+// host mirror of FastShape<M,PPT>: table layout {pre[0..M], tw1[(t-1)*NS1+k], tw2[(t-1)*NS2+k]}
+static std::vector<cplx> build_fast_tables(int M, int ppt) {
     int lg = 0;
     for (int m = M; m > 1; m >>= 1) ++lg;
-    const int R1 = lg > 5 ? (lg - 5 >= 5 ? 32 : (1 << (lg - 5))) : 1;
-    const int R2 = lg > 10 ? (1 << (lg - 10)) : 1;
-    const int NS1 = 32, NS2 = 32 * R1;
+    const int lp = ppt == 16 ? 4 : 5;
+    const int R1 = lg > lp ? (lg - lp >= lp ? ppt : (1 << (lg - lp))) : 1;
+    const int R2 = lg > 2 * lp ? (1 << (lg - 2 * lp)) : 1;
+    const int NS1 = ppt, NS2 = ppt * R1;
     std::vector<cplx> t;
     auto push = [&](double num, double den) {
         const double a = 2.0 * M_PI * num / den;
@@ -524,8 +525,15 @@ int litho_plan_create_ex(int pn, int N, const int* bbox, int flags, litho_plan_t
     int Mf = 32;
     while (Mf < S - 1) Mf <<= 1;
     if (!(flags & LITHO_PLAN_GENERIC) && Mf <= 4096 && 2 * Mf <= N) {
-        std::vector<cplx> tab = build_fast_tables(Mf);
-        if ((int)tab.size() != dispatch_fast_ntab(Mf)) {
+        // points per thread of the fast FFTs: 32 (one exchange, 128 regs) or 16 (two exchanges, 64 regs,
+        // twice the resident warps); LITHO_FAST_PPT overrides the per-size default for experiments
+        p->ppt = 32;
+        if (const char* env = getenv("LITHO_FAST_PPT")) {
+            if (atoi(env) == 16) p->ppt = 16;
+            if (atoi(env) == 32) p->ppt = 32;
+        }
+        std::vector<cplx> tab = build_fast_tables(Mf, p->ppt);
+        if ((int)tab.size() != dispatch_fast_ntab(Mf, p->ppt)) {
             delete p;
             return fail(LITHO_ERR_ARG, "plan_create: internal table layout mismatch");
         }
@@ -738,16 +746,16 @@ int litho_abbe_fft_accumulate_ex(const litho_plan_t* p, const void* maskFT, cons
 #if !defined(LITHO_EMU)
             if (overlap) {
                 if (b >= 2) BE_CHECK((int)cudaStreamWaitEvent(p->aux_stream, p->ev_cols[b & 1], 0));
-                BE_CHECK(dispatch_fast_rows(p->Mf, fr, p->n_sm * 2, p->aux_stream));
+                BE_CHECK(dispatch_fast_rows(p->Mf, p->ppt, fr, p->n_sm * (p->ppt == 16 ? 4 : 2), p->aux_stream));
                 BE_CHECK((int)cudaEventRecord(p->ev_rows[b & 1], p->aux_stream));
                 BE_CHECK((int)cudaStreamWaitEvent(st, p->ev_rows[b & 1], 0));
-                BE_CHECK(dispatch_fast_cols(p->Mf, fc, st));
+                BE_CHECK(dispatch_fast_cols(p->Mf, p->ppt, fc, st));
                 BE_CHECK((int)cudaEventRecord(p->ev_cols[b & 1], st));
                 continue;
             }
 #endif
-            if (phases & 1) BE_CHECK(dispatch_fast_rows(p->Mf, fr, p->n_sm * 2, st));
-            if (phases & 2) BE_CHECK(dispatch_fast_cols(p->Mf, fc, st));
+            if (phases & 1) BE_CHECK(dispatch_fast_rows(p->Mf, p->ppt, fr, p->n_sm * (p->ppt == 16 ? 4 : 2), st));
+            if (phases & 2) BE_CHECK(dispatch_fast_cols(p->Mf, p->ppt, fc, st));
         }
         if ((phases & 2) && p->q > 1 && (p->rim_row || p->rim_col)) {
             RimParams rm;

@@ -58,6 +58,7 @@ struct EmuCtx {
     // a warp barrier is emulated by the (stronger) CTA-wide phase boundary; every thread of the CTA
     // executes the same number of them in the kernels that use it
     void sync_warp() const { fiber_yield(); }
+    void sync_named(int, int) const { fiber_yield(); }
 };
 
 // run one CTA of `nthreads` fibers; body(ctx) is the kernel body bound to its parameters
