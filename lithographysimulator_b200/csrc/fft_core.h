@@ -56,8 +56,15 @@ LITHO_HD void dft_all(cplx (&v)[PPT]) {
 }
 
 // One Stockham pass.  PASS is the pass index, NS the product of the previous radices.
-template <int M, int PPT, int PASS, bool FWD, class Tw, class Sync>
-LITHO_HD void fft_pass(cplx (&v)[PPT], cplx* sm, int es, int g, const Tw& tw, const Sync& sync) {
+// Hook: hook.after_last_gather() runs once per FFT right after the last read of the exchange buffer
+// (before the last butterflies), i.e. at the point from which the buffer is free again -- the fast
+// column kernel uses it to start the asynchronous copy of its next input tile into that buffer.
+struct NoHook {
+    LITHO_HD void after_last_gather() const {}
+};
+
+template <int M, int PPT, int PASS, bool FWD, class Tw, class Sync, class Hook>
+LITHO_HD void fft_pass(cplx (&v)[PPT], cplx* sm, int es, int g, const Tw& tw, const Sync& sync, const Hook& hook) {
     using Sh = FftShape<M, PPT>;
     constexpr int R = Sh::radix(PASS);
     constexpr int NS = Sh::ns(PASS);
@@ -65,11 +72,13 @@ LITHO_HD void fft_pass(cplx (&v)[PPT], cplx* sm, int es, int g, const Tw& tw, co
     constexpr int TG = Sh::TG;
     constexpr bool LAST = (PASS == Sh::NP - 1);
 
+    if constexpr (PASS == 0 && LAST) hook.after_last_gather();  // single pass: the buffer is never used
     if constexpr (PASS > 0) {
         // gather this pass's inputs: element g + TG*e -> register e
         sync.sync();
 #pragma unroll
         for (int e = 0; e < PPT; ++e) v[e] = sm[padp<PPT>(g + TG * e) * es];
+        if constexpr (LAST) hook.after_last_gather();
         // twiddle: butterfly b has index j = g + b*TG, k = j mod NS, angle 2*pi*t*k/(NS*R)
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
@@ -97,16 +106,17 @@ LITHO_HD void fft_pass(cplx (&v)[PPT], cplx* sm, int es, int g, const Tw& tw, co
 #pragma unroll
             for (int t = 0; t < R; ++t) sm[padp<PPT>(base + t * NS) * es] = v[b + t * NB];
         }
-        fft_pass<M, PPT, PASS + 1, FWD>(v, sm, es, g, tw, sync);
+        fft_pass<M, PPT, PASS + 1, FWD>(v, sm, es, g, tw, sync, hook);
     }
     // LAST: j < M/R = NS so k = j and the output index is g + TG*(b + t*NB): register e holds
     // element g + TG*e again.
 }
 
 // Full transform.  Every thread of the sync scope must call this the same number of times.
-template <int M, int PPT, bool FWD, class Tw, class Sync>
-LITHO_HD void fft_run(cplx (&v)[PPT], cplx* sm, int es, int g, const Tw& tw, const Sync& sync) {
-    fft_pass<M, PPT, 0, FWD>(v, sm, es, g, tw, sync);
+template <int M, int PPT, bool FWD, class Tw, class Sync, class Hook = NoHook>
+LITHO_HD void fft_run(cplx (&v)[PPT], cplx* sm, int es, int g, const Tw& tw, const Sync& sync,
+                      const Hook& hook = Hook()) {
+    fft_pass<M, PPT, 0, FWD>(v, sm, es, g, tw, sync, hook);
 }
 
 // Twiddles from the global table w_L[i] = exp(+2*pi*i*i/L), L = M*twscale (generic kernels).

@@ -76,6 +76,14 @@ struct DevCtx {
     __device__ __forceinline__ int gdx() const { return gridDim.x; }
     __device__ __forceinline__ void sync() const { __syncthreads(); }
     __device__ __forceinline__ void sync_warp() const { __syncwarp(); }
+    // 16-byte asynchronous global -> shared copy (LDGSTS), and the wait for all of this thread's copies
+    __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) const {
+        const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+    }
+    __device__ __forceinline__ void cp_async_wait() const {
+        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+    }
     // named barrier over `n` threads (a multiple of 32); id 0 is __syncthreads' barrier, use 1..15
     __device__ __forceinline__ void sync_named(int id, int n) const {
         asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");

@@ -59,6 +59,9 @@ struct EmuCtx {
     // executes the same number of them in the kernels that use it
     void sync_warp() const { fiber_yield(); }
     void sync_named(int, int) const { fiber_yield(); }
+    // asynchronous copies complete immediately in the emulation
+    void cp_async16(void* dst, const void* src) const { memcpy(dst, src, 16); }
+    void cp_async_wait() const {}
 };
 
 // run one CTA of `nthreads` fibers; body(ctx) is the kernel body bound to its parameters
