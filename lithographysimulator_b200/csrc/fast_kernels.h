@@ -198,89 +198,57 @@ LITHO_HD void fast_rows_body(const FastRowsParams& P, const Ctx& ctx, cplx* smem
     }
 }
 
-// Asynchronous copy of one source point's input tile (rows 0..Sr-1 x CB columns of T) into the exchange
-// buffer, dense [u][CB] layout.  Issued from the FFT hook as soon as the buffer is free, so the copy
-// overlaps the last butterflies and the |E|^2 accumulation instead of stalling the next iteration.
-template <int M, int PPT, class Ctx>
-struct ColPrefetch {
-    const Ctx& ctx;
-    cplx* buf;          // exchange buffer base (column 0)
-    const cplx* next;   // T + tile origin of the next source point, or null
-    int Sr;
-    LITHO_HD void issue() const {
-        constexpr int CB = FastShape<M, PPT>::CB;
-        constexpr int CPR = CB / 2;  // 16-byte chunks per tile row
-        if (next == nullptr) return;
-        for (int i = ctx.tid(); i < Sr * CPR; i += ctx.bdim()) {
-            const int row = i / CPR, c = i - row * CPR;
-            ctx.cp_async16(buf + (size_t)row * CB + 2 * c, next + (size_t)row * M + 2 * c);
-        }
-    }
-    LITHO_HD void after_last_gather() const {
-        ctx.sync();  // every thread has read its exchange data: the buffer may be overwritten
-        issue();
-    }
-};
-
 // grid.x = 2*M/CB column blocks (rc major), grid.y = 2 (rr), block = COL_THREADS
 template <int M, int PPT, class Ctx>
 LITHO_HD void fast_cols_body(const FastColsParams& P, const Ctx& ctx, cplx* smem) {
     using F = FastShape<M, PPT>;
     constexpr int TG = F::TG;
     constexpr int CB = F::CB;
-    static_assert(CB % 2 == 0, "tile rows are copied in 16-byte chunks");
     cplx* tab = smem;
+    fast_load_tables<M, PPT>(P.tables, tab, ctx);
     const int col = ctx.tid() % CB;
     const int g = ctx.tid() / CB;
-    cplx* buf = smem + F::NTAB_PAD;
-    cplx* ex = buf + col;
+    cplx* ex = smem + F::NTAB_PAD + col;
     const int rr = ctx.by();
     constexpr int NBLK = M / CB;
     const int rc = ctx.bx() / NBLK;
-    const int kc0 = (ctx.bx() - rc * NBLK) * CB;
-    const int kc = kc0 + col;
+    const int kc = (ctx.bx() - rc * NBLK) * CB + col;
     const SmemTw<M, PPT> tw{tab};
     const GroupSync<Ctx, 2> gs{ctx, 0, 0};
-    const size_t tile_stride = (size_t)2 * P.Sr * M;              // between consecutive source points
-    const cplx* tile0 = P.T + ((size_t)rc * P.Sr) * M + kc0;      // tile of source point 0
-
-    // first tile in flight while the twiddle tables are loaded
-    ColPrefetch<M, PPT, Ctx>{ctx, buf, tile0, P.Sr}.issue();
-    fast_load_tables<M, PPT>(P.tables, tab, ctx);
 
     float acc[PPT];
 #pragma unroll
     for (int e = 0; e < PPT; ++e) acc[e] = 0.f;
-    const int last = P.Sr - 1;
 
     for (int sl = 0; sl < P.batch; ++sl) {
-        ctx.cp_async_wait();
-        ctx.sync();  // tile of source point sl is in shared memory
+        const cplx* src = P.T + ((size_t)(sl * 2 + rc) * P.Sr) * M + kc;
         cplx v[PPT];
-        if (last >= M - 1) {  // common case: every slot has an input
+        const int last = P.Sr - 1;
+        const cplx* srcg = src + (size_t)g * M;
+        // Branch-free loads so that all of them are in flight together (one load-use round trip per
+        // FFT, not per element).  Common case Sr >= M: every slot has an input, no masking needed.
+        if (last >= M - 1) {
 #pragma unroll
-            for (int e = 0; e < PPT; ++e) v[e] = ex[(size_t)(g + TG * e) * CB];
+            for (int e = 0; e < PPT; ++e) v[e] = ldg_c(srcg + (size_t)e * (TG * M));
         } else {
 #pragma unroll
             for (int e = 0; e < PPT; ++e) {
                 const int u = g + TG * e;
-                const cplx x = ex[(size_t)(u <= last ? u : last) * CB];
+                const cplx* pa = (u <= last) ? srcg + (size_t)e * (TG * M) : src + (size_t)last * M;
+                const cplx x = ldg_c(pa);
                 v[e] = mk(u <= last ? x.x : 0.f, u <= last ? x.y : 0.f);
             }
         }
-        if (P.Sr > M) {  // rim input u = M folds onto slot 0 with w_2M^(rr*M) = (-1)^rr
-            const cplx y = ex[(size_t)M * CB];
+        if (rr) {
+#pragma unroll
+            for (int e = 0; e < PPT; ++e) v[e] = cmul(v[e], tab[F::PRE_OFF + g + TG * e]);
+        }
+        if (P.Sr > M) {
+            const cplx y = ldg_c(src + (size_t)M * M);
             const float sgn = (g == 0) ? (rr ? -1.f : 1.f) : 0.f;
             v[0] = mk(v[0].x + sgn * y.x, v[0].y + sgn * y.y);
         }
-        if (rr) {
-#pragma unroll
-            for (int e = 1; e < PPT; ++e) v[e] = cmul(v[e], tab[F::PRE_OFF + g + TG * e]);
-            if (g != 0) v[0] = cmul(v[0], tab[F::PRE_OFF + g]);  // slot 0 already carries both of its inputs
-        }
-        // (the first barrier inside fft_run orders these tile reads before the exchange writes)
-        const cplx* next = (sl + 1 < P.batch) ? tile0 + (size_t)(sl + 1) * tile_stride : nullptr;
-        fft_run<M, PPT, false>(v, ex, CB, g, tw, gs, ColPrefetch<M, PPT, Ctx>{ctx, buf, next, P.Sr});
+        fft_run<M, PPT, false>(v, ex, CB, g, tw, gs);
         const float w = P.weights ? P.weights[P.s_begin + sl] : 1.f;
 #pragma unroll
         for (int e = 0; e < PPT; ++e) acc[e] += w * cnorm2(v[e]);
