@@ -260,6 +260,8 @@ static int get_twiddles(int L, cplx** out) {
 }
 
 // --------------------------------------------------------------------------- plan
+// T ring slots of the fast path: rows(b) may run LITHO_TSLOTS-1 batches ahead of cols(b)
+#define LITHO_TSLOTS 3
 struct litho_plan {
     int pn, N;
     int bbox[4];
@@ -278,7 +280,7 @@ struct litho_plan {
     int n_sm;
 #if !defined(LITHO_EMU)
     cudaStream_t aux_stream;  // row passes of the fast path run here, overlapping the column passes
-    cudaEvent_t ev_start, ev_rows[2], ev_cols[2];
+    cudaEvent_t ev_start, ev_rows[LITHO_TSLOTS], ev_cols[LITHO_TSLOTS];
 #endif
 };
 
@@ -551,7 +553,7 @@ int litho_plan_create_ex(int pn, int N, const int* bbox, int flags, litho_plan_t
         {
             cudaError_t e = cudaStreamCreateWithFlags(&p->aux_stream, cudaStreamNonBlocking);
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming);
-            for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+            for (int i = 0; i < LITHO_TSLOTS && e == cudaSuccess; ++i) {
                 e = cudaEventCreateWithFlags(&p->ev_rows[i], cudaEventDisableTiming);
                 if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_cols[i], cudaEventDisableTiming);
             }
@@ -589,7 +591,7 @@ void litho_plan_destroy(litho_plan_t* p) {
         cudaStreamSynchronize(p->aux_stream);
         cudaStreamDestroy(p->aux_stream);
         cudaEventDestroy(p->ev_start);
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < LITHO_TSLOTS; ++i) {
             cudaEventDestroy(p->ev_rows[i]);
             cudaEventDestroy(p->ev_cols[i]);
         }
@@ -637,7 +639,7 @@ size_t litho_plan_workspace_bytes(const litho_plan_t* p, int batch) {
     if (!p) return 0;
     if (batch <= 0) batch = p->default_batch;
     if (p->path == 2) {
-        const size_t fast = (size_t)2 * batch * 2 * p->Sr * p->Mf * sizeof(cplx);  // two T slots (double buffer)
+        const size_t fast = (size_t)LITHO_TSLOTS * batch * 2 * p->Sr * p->Mf * sizeof(cplx);  // T slots (ring)
         const size_t gen1 = generic_t_bytes(p, 1);
         return fast > gen1 ? fast : gen1;
     }
@@ -724,11 +726,12 @@ int litho_abbe_fft_accumulate_ex(const litho_plan_t* p, const void* maskFT, cons
         fc.ic = intensity;
         // T is double-buffered: the row pass of batch b+1 runs on the plan's auxiliary stream while the
         // column pass of batch b runs on the caller's stream, so the tail of one kernel overlaps the head
-        // of the other (both are short, ~20-40 us at cfg3).  rows(b) -> cols(b) and cols(b) -> rows(b+2)
+        // of the other (both are short, ~20-40 us at cfg3).  rows(b) -> cols(b) and cols(b) -> rows(b+LITHO_TSLOTS)
         // (slot reuse) are ordered with events; all column passes stay on one stream, which also
         // serialises their read-modify-write of the intensity plane.
         const size_t slot_elems = (size_t)batch * 2 * p->Sr * p->Mf;
-        cplx* Tslot[2] = {(cplx*)workspace, (cplx*)workspace + slot_elems};
+        cplx* Tslot[LITHO_TSLOTS];
+        for (int i = 0; i < LITHO_TSLOTS; ++i) Tslot[i] = (cplx*)workspace + (size_t)i * slot_elems;
 #if !defined(LITHO_EMU)
         const bool overlap = (phases == 3) && p->aux_stream != nullptr;
         if (overlap) {
@@ -741,16 +744,16 @@ int litho_abbe_fft_accumulate_ex(const litho_plan_t* p, const void* maskFT, cons
         int b = 0;
         for (int s0 = 0; s0 < n_src; s0 += batch, ++b) {
             const int nb = (n_src - s0) < batch ? (n_src - s0) : batch;
-            fr.s_begin = s0; fr.batch = nb; fr.T = Tslot[b & 1];
-            fc.s_begin = s0; fc.batch = nb; fc.T = Tslot[b & 1];
+            fr.s_begin = s0; fr.batch = nb; fr.T = Tslot[b % LITHO_TSLOTS];
+            fc.s_begin = s0; fc.batch = nb; fc.T = Tslot[b % LITHO_TSLOTS];
 #if !defined(LITHO_EMU)
             if (overlap) {
-                if (b >= 2) BE_CHECK((int)cudaStreamWaitEvent(p->aux_stream, p->ev_cols[b & 1], 0));
+                if (b >= LITHO_TSLOTS) BE_CHECK((int)cudaStreamWaitEvent(p->aux_stream, p->ev_cols[b % LITHO_TSLOTS], 0));
                 BE_CHECK(dispatch_fast_rows(p->Mf, p->ppt, fr, p->n_sm * (p->ppt == 16 ? 4 : 2), p->aux_stream));
-                BE_CHECK((int)cudaEventRecord(p->ev_rows[b & 1], p->aux_stream));
-                BE_CHECK((int)cudaStreamWaitEvent(st, p->ev_rows[b & 1], 0));
+                BE_CHECK((int)cudaEventRecord(p->ev_rows[b % LITHO_TSLOTS], p->aux_stream));
+                BE_CHECK((int)cudaStreamWaitEvent(st, p->ev_rows[b % LITHO_TSLOTS], 0));
                 BE_CHECK(dispatch_fast_cols(p->Mf, p->ppt, fc, st));
-                BE_CHECK((int)cudaEventRecord(p->ev_cols[b & 1], st));
+                BE_CHECK((int)cudaEventRecord(p->ev_cols[b % LITHO_TSLOTS], st));
                 continue;
             }
 #endif
