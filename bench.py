@@ -243,6 +243,25 @@ def run_ours(args):
     ms_per_step = ms / args.steps
     value = 1000.0 / ms_per_step
 
+    # ---- phase breakdown of one image (events on the current stream, after the timed region) ----
+    def timed(fn, reps=3):
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize(dev)
+        return a.elapsed_time(b) / reps
+
+    inten_b = eng.intensity_plane(plan)
+    breakdown = {
+        "zero_plane": timed(lambda: eng.intensity_plane(plan)),
+        "accumulate": timed(lambda: eng.accumulate(plan, mft_d, pf_d, shifts_mine, inten_b, None, args.batch)),
+        "all_reduce": timed(lambda: reduce_fn(inten_b)) if world > 1 else 0.0,
+        "finalize": timed(lambda: eng.finalize(plan, inten_b, eps)),
+    }
+
     # ---- per-kernel timing (live, CUDA events on the launching stream, after the timed region) ----
     inten = eng.intensity_plane(plan)
     n_mine = int(shifts_mine.shape[0])
@@ -359,7 +378,8 @@ def run_ours(args):
                                                                            "one NCCL all-reduce of the intensity plane"},
                 "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
                 "e2e": {"value": 1.0 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-                "roofline": roofline, "cpu_baseline": cpu, "wall_s_timed_region": t_wall}
+                "roofline": roofline, "cpu_baseline": cpu, "breakdown_ms": breakdown,
+                "wall_s_timed_region": t_wall}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

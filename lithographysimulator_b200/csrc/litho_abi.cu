@@ -508,7 +508,6 @@ int litho_plan_create_ex(int pn, int N, const int* bbox, int flags, litho_plan_t
         delete p;
         return fail(LITHO_ERR_CUDA, std::string("plan_create: twiddle table: ") + be_errstr(rc));
     }
-    // batch: keep T for one launch pair around 64 MB (L2-resident on B200), at least 1, at most 16
     size_t per = (size_t)p->zp.R * p->Sr * p->zp.Wr * sizeof(cplx);
     // ---- fast path eligibility: even window fit S <= Mf+1, coarse grid Nc = 2*Mf no finer than N ----
     p->path = 1; p->tables = nullptr; p->Mf = p->Nc = p->q = 0; p->rim_row = p->rim_col = 0;
@@ -576,8 +575,12 @@ int litho_plan_create_ex(int pn, int N, const int* bbox, int flags, litho_plan_t
         p->ext[6] = clampi(e[6] - r0, 0, p->Sr - 1); p->ext[7] = clampi(e[7] - r0, 0, p->Sr - 1);  // last column
         per = (size_t)2 * p->Sr * Mf * sizeof(cplx);
     }
-    // batch: keep T for one launch pair around 64 MB (L2-resident on B200), at least 1, at most 16
-    int b = (int)((64u << 20) / (per ? per : 1));
+    // batch (source points per launch pair).  Generic path: T of one batch around 64 MB.  Fast path:
+    // measured on B200 at cfg3 (profiles/): launches of 3 source points (T in L2) lose more to launch
+    // gaps, table loads and partial waves than batches of 12 lose to T spilling to HBM (47 vs 54.5
+    // images/s), so aim at ~200 MB per slot, at least 1, at most 16.
+    const size_t target = (p->path == 2) ? ((size_t)208 << 20) : ((size_t)64 << 20);
+    int b = (int)(target / (per ? per : 1));
     p->default_batch = b < 1 ? 1 : (b > 16 ? 16 : b);
     *out = p;
     return LITHO_OK;

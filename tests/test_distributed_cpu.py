@@ -1,0 +1,78 @@
+"""World-size-2 check of the multi-GPU scheme on CPU (gloo): source points sharded across ranks, each rank
+accumulates a partial intensity plane through the C ABI (CPU emulation of the kernels -- test
+infrastructure), one sum all-reduce, post-processing after the reduce.  Must equal the single-process image
+and the reference golden."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import helpers as H
+from oracle import abbe_oracle as O
+from lithographysimulator_b200.distributed import shard_shifts
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, case, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        c = H.load_kat()[case]
+        lib = H.emu_lib()
+        pn = c["maskFT"].shape[0]
+        ps = float(c["pixel_size"])
+        eps, N = lib.epsilon_n(4 / pn, ps, 193.0)
+        mft = np.ascontiguousarray(c["maskFT"])
+        pup = np.ascontiguousarray(c["pupil"])
+        shifts_all = np.ascontiguousarray(O.source_shifts(c["lightsource"], pn))
+        support = lib.pupil_support(pup.ctypes.data, pn)
+        # plan chosen from ALL source points so that both ranks use the same intensity layout
+        plan = lib.plan_create(pn, N, support)
+        if plan.path == 2 and not plan.shifts_fit(lib.shift_bounds(shifts_all.ctypes.data, len(shifts_all))):
+            plan = lib.plan_create(pn, N, support, 1)
+        mine = np.ascontiguousarray(shard_shifts(torch.from_numpy(shifts_all), rank, world).numpy())
+        inten = np.zeros(plan.intensity_elems, np.float32)
+        wsb = plan.workspace_bytes(0)
+        ws = np.zeros(max(wsb, 8), np.uint8)
+        plan.accumulate(mft.ctypes.data, pup.ctypes.data, mine.ctypes.data, None, len(mine), 0, inten.ctypes.data,
+                        ws.ctypes.data, wsb)
+        t = torch.from_numpy(inten)
+        dist.all_reduce(t)  # sum of the partial planes (NCCL over NVLink on the GPU box)
+        side = plan.output_side(eps)
+        out = np.zeros((side, side), np.float32)
+        fwb = plan.finalize_workspace_bytes()
+        fws = np.zeros(max(fwb, 8), np.uint8)
+        plan.finalize(inten.ctypes.data, eps, out.ctypes.data, fws.ctypes.data, fwb)
+        if rank == 0:
+            np.save(out_path, out)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case", ["demo64_quasar", "wrap_128"])
+def test_two_rank_sharded_image_matches_reference(tmp_path, case):
+    H.emu_lib()  # build once before forking
+    out_path = str(tmp_path / "img.npy")
+    mp.spawn(_worker, args=(2, _free_port(), case, out_path), nprocs=2, join=True)
+    img = np.load(out_path)
+    ref = H.load_kat()[case]["image"]
+    assert img.shape == ref.shape
+    assert O.rel_l2(img, ref) < H.TOL
+
+
+def test_shard_shifts_partition():
+    sh = torch.arange(46).reshape(23, 2)
+    parts = [shard_shifts(sh, r, 4) for r in range(4)]
+    assert sum(len(p) for p in parts) == 23 and max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+    merged = torch.cat(parts).tolist()
+    assert sorted(merged) == sh.tolist()
