@@ -139,6 +139,17 @@ int litho_direct_field(const void* A, const void* pupil, const void* maskFT, int
 int litho_direct_mask_spectrum(const void* Aplus, const int16_t* geometry, int pn, void* maskFT, void* workspace,
                                size_t workspace_bytes, void* stream);
 
+/* LightSource.generateAnnular / generateQuasar                    lightsource.py:34-73
+ * fp16 sigma grid replayed op by op; out = pn x pn int64 0/1.  quasar_count = 0 selects the annulus. */
+int litho_source_build(int pn, double sigma_in, double sigma_out, double shift_x, double shift_y, int quasar_count,
+                       double rotation, int64_t* out, void* stream);
+
+/* generateWavefrontError + generatePhi                                pupil.py:46-111
+ * aberrations_host: n_ab OSA-indexed coefficients (HOST floats holding fp16 values, AFTER the caller applied
+ * the reference's in-place defocus rescale aberrations[4] *= NA^2/(4*lambda), pupil.py:91-92).
+ * pupil / wavefront: pn x pn complex64 outputs, either may be NULL.  Synchronises `stream`. */
+int litho_pupil_build(const float* aberrations_host, int n_ab, int pn, void* pupil, void* wavefront, void* stream);
+
 /* FP32 FMA throughput probe (roofline denominator measured in the same run): launches `blocks` CTAs
  * of 256 threads, each thread doing iters*16 dependent-chain FMAs; *flops receives the flop count. */
 int litho_fp32_probe(float* out, int blocks, int iters, double* flops, void* stream);

@@ -53,6 +53,8 @@ SYMBOLS = [
                                           C.c_size_t, _P]),
     ("litho_direct_field", C.c_int, [_P, _P, _P, C.c_int, C.POINTER(C.c_int), _P, _P, C.c_size_t, _P]),
     ("litho_direct_mask_spectrum", C.c_int, [_P, _P, C.c_int, _P, _P, C.c_size_t, _P]),
+    ("litho_source_build", C.c_int, [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_double, _P, _P]),
+    ("litho_pupil_build", C.c_int, [C.POINTER(C.c_float), C.c_int, C.c_int, _P, _P, _P]),
     ("litho_fp32_probe", C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_double), _P]),
     ("litho_fft_output_side", C.c_int, [C.c_int, C.c_double]),
     ("litho_abbe_fft_finalize", C.c_int, [_P, _P, C.c_double, _P, _P, C.c_size_t, _P]),

@@ -13,6 +13,7 @@
 
 #include "launch.h"
 #include "direct_kernels.h"
+#include "builders.h"
 
 #if defined(LITHO_EMU)
 #include "emu_runtime.h"
@@ -203,6 +204,14 @@ template <int EPI>
 __global__ void __launch_bounds__(DIRECT_THREADS) direct_cols_kernel(const __grid_constant__ DirectParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     direct_cols_body<EPI>(P, DevCtx{}, reinterpret_cast<cplx*>(smem_raw));
+}
+__global__ void source_kernel(const __grid_constant__ SourceParams P) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < P.pn) source_pixel(P, blockIdx.y, j);
+}
+__global__ void pupil_kernel(const __grid_constant__ PupilParams P) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < P.pn) pupil_pixel(P, blockIdx.y, j);
 }
 __global__ void resample_kernel(const __grid_constant__ ResampleParams P) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1215,6 +1224,98 @@ int litho_direct_mask_spectrum(const void* Aplus, const int16_t* geometry, int p
     P.pr0 = 0; P.pc0 = 0; P.Sr = pn; P.Sc = pn;
     P.batch = 1; P.T = (cplx*)workspace; P.field = (cplx*)maskFT;
     BE_CHECK(direct_launch(DIRECT_GEOMETRY, DIRECT_FIELD, P, (litho_stream_t)stream));
+    return LITHO_OK;
+}
+
+// ---------------------------------------------------------------------------- builders
+int litho_source_build(int pn, double sigma_in, double sigma_out, double shift_x, double shift_y, int quasar_count,
+                       double rotation, int64_t* out, void* stream) {
+    if (!out || pn < 1 || quasar_count < 0 || quasar_count > 16)
+        return fail(LITHO_ERR_ARG, "source_build: bad argument (quasar_count must be 0..16)");
+    SourceParams P;
+    memset(&P, 0, sizeof(P));
+    P.pn = pn;
+    const double span = 2.0;
+    P.x_start = (float)(-span - shift_x);
+    P.y_start = (float)(-span - shift_y);
+    P.step = (float)(span * 2.0 / (double)pn);
+    P.sigma_in = round_f16((float)sigma_in);
+    P.sigma_out = round_f16((float)sigma_out);
+    P.quasar = quasar_count > 0;
+    P.count = quasar_count;
+    P.rotation = (float)rotation;
+    P.two_pi = round_f16((float)(2.0 * M_PI));
+    if (quasar_count > 0) {
+        const double spacing = M_PI / (double)quasar_count;
+        for (int g = 0; g < quasar_count; ++g) {
+            P.spacing_lo[g] = round_f16((float)((double)(g + g) * spacing));
+            P.spacing_hi[g] = round_f16((float)((double)(g + g + 1) * spacing));
+        }
+    }
+    P.out = out;
+#if defined(LITHO_EMU)
+    (void)stream;
+    for (int i = 0; i < pn; ++i)
+        for (int j = 0; j < pn; ++j) source_pixel(P, i, j);
+#else
+    source_kernel<<<dim3((pn + 255) / 256, pn, 1), 256, 0, (litho_stream_t)stream>>>(P);
+    BE_CHECK((int)cudaGetLastError());
+#endif
+    return LITHO_OK;
+}
+
+static double factorial_d(int n) {
+    double f = 1.0;
+    for (int i = 2; i <= n; ++i) f *= (double)i;
+    return f;
+}
+
+int litho_pupil_build(const float* aberrations_host, int n_ab, int pn, void* pupil, void* wavefront, void* stream) {
+    if (!aberrations_host || n_ab < 1 || n_ab > 256 || pn < 1 || (!pupil && !wavefront))
+        return fail(LITHO_ERR_ARG, "pupil_build: bad argument");
+    std::vector<ZernikeTerm> terms(n_ab);
+    for (int j = 0; j < n_ab; ++j) {
+        ZernikeTerm& z = terms[j];
+        memset(&z, 0, sizeof(z));
+        // OSA/ANSI index -> (m, n), pupil.py:82-86
+        const int n = (int)ceil(0.5 * (-3.0 + sqrt(9.0 + 8.0 * (double)j)));
+        const int m = 2 * j - n * (n + 2);
+        const int am = m < 0 ? -m : m;
+        const int lo = (n - am) / 2, hi = (n + am) / 2;
+        if (lo + 1 > 8) return fail(LITHO_ERR_ARG, "pupil_build: radial order too high (n <= 15 supported)");
+        z.m = m; z.n = n; z.nk = lo + 1;
+        for (int k = 0; k <= lo; ++k) {
+            const double c = ((k & 1) ? -1.0 : 1.0) * factorial_d(n - k) /
+                             (factorial_d(k) * factorial_d(hi - k) * factorial_d(lo - k));
+            z.stat[k] = (float)c;
+            z.expo[k] = n - 2 * k;
+        }
+        const double nmn = sqrt((2.0 * n + 1.0) / (1.0 + (m == 0 ? 1.0 : 0.0)));
+        const float coeff = round_f16(aberrations_host[j]);
+        z.cn = round_f16(coeff * (float)(m >= 0 ? nmn : -nmn));
+    }
+    litho_stream_t st = (litho_stream_t)stream;
+    ZernikeTerm* dterms = nullptr;
+    BE_CHECK(be_malloc((void**)&dterms, sizeof(ZernikeTerm) * n_ab));
+    int rc = be_h2d(dterms, terms.data(), sizeof(ZernikeTerm) * n_ab, st);
+    PupilParams P;
+    memset(&P, 0, sizeof(P));
+    P.pn = pn; P.start = -2.0f; P.step = (float)(4.0 / (double)pn);
+    P.n_terms = n_ab; P.terms = dterms;
+    P.two_pi_f = (float)(2.0 * M_PI);
+    P.pupil = (cplx*)pupil; P.we = (cplx*)wavefront;
+    if (rc == 0) {
+#if defined(LITHO_EMU)
+        for (int i = 0; i < pn; ++i)
+            for (int j = 0; j < pn; ++j) pupil_pixel(P, i, j);
+#else
+        pupil_kernel<<<dim3((pn + 255) / 256, pn, 1), 256, 0, st>>>(P);
+        rc = (int)cudaGetLastError();
+        if (rc == 0) rc = (int)cudaStreamSynchronize(st);  // the term table is freed below
+#endif
+    }
+    be_free(dterms);
+    if (rc != 0) return fail(LITHO_ERR_CUDA, std::string("pupil_build: ") + be_errstr(rc));
     return LITHO_OK;
 }
 

@@ -91,12 +91,25 @@ class LightSource:
         self.shiftX = shiftX
         self.shiftY = shiftY
 
+    def _build(self, count: int, rotation: float) -> torch.Tensor:
+        from . import _native
+        lib = _native.device_lib()
+        pn = int(self.pixelNumber)
+        with torch.cuda.device(self.device):
+            out = torch.empty((pn, pn), dtype=torch.int64, device=self.device)
+            lib.check(lib.litho_source_build(pn, float(self.sigmaInner), float(self.sigmaOuter), float(self.shiftX),
+                                             float(self.shiftY), int(count), float(rotation), out.data_ptr(),
+                                             torch.cuda.current_stream(self.device).cuda_stream), "litho_source_build")
+        return out
+
     def generateAnnular(self) -> torch.Tensor:
-        """1 where sigmaInner <= |sigma| <= sigmaOuter, int64 (lightsource.py:34-50)."""
-        return annular_source(self.sigmaInner, self.sigmaOuter, self.pixelNumber, self.shiftX, self.shiftY, self.device)
+        """1 where sigmaInner <= |sigma| <= sigmaOuter, int64 (lightsource.py:34-50); native kernel."""
+        return self._build(0, 0.0)
 
     def generateQuasar(self, count, rotation) -> torch.Tensor:
-        """Annulus with `count` angular gaps removed (lightsource.py:52-73)."""
+        """Annulus with `count` angular gaps removed (lightsource.py:52-73); native kernel for count <= 16."""
+        if 1 <= int(count) <= 16:
+            return self._build(int(count), float(rotation))
         return quasar_source(self.sigmaInner, self.sigmaOuter, self.pixelNumber, count, rotation, self.shiftX,
                              self.shiftY, self.device)
 
@@ -165,6 +178,10 @@ def generateWavefrontError(aberrations, pixelNumber, NA, wavelength, device):
     aberrations[4] (defocus, nm) by NA^2/(4 lambda) IN PLACE on the caller's tensor (Q4)."""
     if len(aberrations) >= 4:
         aberrations[4] = aberrations[4] * NA ** 2 / (4 * wavelength)
+    return _wavefront_from_scaled(aberrations, pixelNumber, device)
+
+
+def _wavefront_from_scaled(aberrations, pixelNumber, device):
     r, theta = _polar_grid(pixelNumber, device)
     we = torch.zeros((pixelNumber, pixelNumber), dtype=torch.float16, device=device)
     for j in range(len(aberrations)):
@@ -194,8 +211,31 @@ class Pupil:
         self.wavelength = wavelength
         self.NA = NA
 
+    def _build(self, want_pupil: bool, want_we: bool):
+        """Native replay of generateWavefrontError + generatePhi (csrc/builders.h).  Like the reference,
+        rescales aberrations[4] IN PLACE on the caller's tensor every time it runs (pupil.py:91-92, Q4)."""
+        import ctypes as C
+        from . import _native
+        ab = self.aberrations
+        if len(ab) >= 4:
+            ab[4] = ab[4] * self.NA ** 2 / (4 * self.wavelength)
+        vals = [float(v) for v in ab.detach().to(torch.float16).float().cpu().tolist()]
+        if len(vals) > 120:  # radial orders beyond the native table: op-by-op torch evaluation
+            we = _wavefront_from_scaled(ab, self.pixelNumber, self.device)
+            return (generatePhi(we, self.pixelNumber, self.device) if want_pupil else None), we
+        lib = _native.device_lib()
+        pn = int(self.pixelNumber)
+        with torch.cuda.device(self.device):
+            pupil = torch.empty((pn, pn), dtype=torch.complex64, device=self.device) if want_pupil else None
+            we = torch.empty((pn, pn), dtype=torch.complex64, device=self.device) if want_we else None
+            arr = (C.c_float * len(vals))(*vals)
+            lib.check(lib.litho_pupil_build(arr, len(vals), pn, None if pupil is None else pupil.data_ptr(),
+                                            None if we is None else we.data_ptr(),
+                                            torch.cuda.current_stream(self.device).cuda_stream), "litho_pupil_build")
+        return pupil, we
+
     def generateWavefrontError(self) -> torch.Tensor:
-        return generateWavefrontError(self.aberrations, self.pixelNumber, self.NA, self.wavelength, self.device)
+        return self._build(False, True)[1]
 
     def generatePupilFunction(self) -> torch.Tensor:
-        return generatePhi(self.generateWavefrontError(), self.pixelNumber, self.device)
+        return self._build(True, False)[0]

@@ -198,7 +198,7 @@ def light_source_annular(sigmaIn, sigmaOut, pn: int, shiftX=0, shiftY=0) -> np.n
 def light_source_quasar(sigmaIn, sigmaOut, pn: int, count: int, rotation: float, shiftX=0, shiftY=0) -> np.ndarray:
     """lightsource.py:52-73 -- annulus times `count` angular cut-outs, all in fp16."""
     sX, sY, O = _sigma_grid(pn, shiftX, shiftY)
-    theta = _h(_h(np.arctan2(sY, sX)) + F32(rotation))
+    theta = _h(_h(np.arctan2(sY.astype(np.float64), sX.astype(np.float64))) + F32(rotation))
     two_pi = _h(2 * math.pi)
     theta = _h(theta - two_pi * np.floor(theta / two_pi))  # python-style remainder, fp16 modulus
     theta = np.where(theta == two_pi, F32(0), theta)
@@ -227,7 +227,9 @@ def _pupil_grid(pn: int):
     X = np.broadcast_to(x[None, :], (pn, pn))
     Y = np.broadcast_to(x[:, None], (pn, pn))
     r = _h(np.sqrt(_h(_h(X * X) + _h(Y * Y))))
-    theta = _h(np.arctan2(Y, X))
+    # transcendental steps are evaluated in float64 and rounded once (float32 libm results differ by an
+    # ulp between hosts; the double-rounded value reproduces the reference's CPU tensors exactly)
+    theta = _h(np.arctan2(Y.astype(np.float64), X.astype(np.float64)))
     return r, theta
 
 
@@ -241,7 +243,7 @@ def _pow_f16(r: np.ndarray, e: int) -> np.ndarray:
         return _h(r * r)
     if e == 3:
         return _h(r * r * r)
-    return _h(np.power(r.astype(F32), F32(e)))
+    return _h(np.power(r.astype(np.float64), float(e)))
 
 
 def generate_z(m: int, n: int, pn: int, coeff_f16: float, grid=None) -> np.ndarray:
@@ -259,10 +261,10 @@ def generate_z(m: int, n: int, pn: int, coeff_f16: float, grid=None) -> np.ndarr
     c = _h(coeff_f16)
     if m >= 0:
         cn = _h(c * F32(Nmn))
-        Z = _h(_h(cn * R) * _h(np.cos(_h(F32(m) * theta))))
+        Z = _h(_h(cn * R) * _h(np.cos(_h(F32(m) * theta).astype(np.float64))))
     else:
         cn = _h(c * F32(-Nmn))
-        Z = _h(_h(cn * R) * _h(np.sin(_h(F32(m) * theta))))
+        Z = _h(_h(cn * R) * _h(np.sin(_h(F32(m) * theta).astype(np.float64))))
     return np.where(r <= 1, Z, F32(0)).astype(F32)
 
 
@@ -287,7 +289,7 @@ def pupil_function(aberrations_f16, pn: int, NA: float, wavelength: float, cdtyp
     WE, ab = wavefront_error(aberrations_f16, pn, NA, wavelength)
     r, _ = _pupil_grid(pn)
     if cdtype == np.complex64:
-        arg = (F32(2 * math.pi) * WE).astype(F32)
+        arg = (F32(2 * math.pi) * WE).astype(F32).astype(np.float64)
         phi = (np.cos(arg) + 1j * np.sin(arg)).astype(np.complex64)
     else:
         arg = 2 * math.pi * WE.astype(np.float64)

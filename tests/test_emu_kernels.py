@@ -176,6 +176,43 @@ def test_emu_direct_field():
     assert np.linalg.norm(field - d["field"]) / np.linalg.norm(d["field"]) < H.TOL
 
 
+def test_emu_builders_match_reference():
+    """LightSource / Pupil builders (fp16 step replay) against the reference's own tensors and the oracle."""
+    import ctypes as C
+    import math
+    from lithographysimulator_b200 import workloads as wl
+    lib = H.emu_lib()
+    c = KAT["demo64_quasar"]
+    out = np.zeros((64, 64), np.int64)
+    lib.check(lib.litho_source_build(64, 0.4, 0.8, 0.0, 0.0, 4, -math.pi / 8, out.ctypes.data, None))
+    assert (out == c["lightsource"]).all()
+    lib.check(lib.litho_source_build(64, 0.4, 0.8, 0.0, 0.0, 0, 0.0, out.ctypes.data, None))
+    assert (out == KAT["demo64_annular"]["lightsource"]).all()
+    out = np.zeros((128, 128), np.int64)
+    lib.check(lib.litho_source_build(128, 0.4, 0.8, 0.5, -0.25, 4, -math.pi / 8, out.ctypes.data, None))
+    assert (out * wl.lattice(128, 7) == KAT["shifted_128"]["lightsource"]).all()
+    for pn, si, so, cnt, rot in ((256, 0.6, 0.9, 0, 0.0), (256, 0.3, 1.3, 3, 0.3), (512, 0.0, 0.6, 5, 1.0)):
+        out = np.zeros((pn, pn), np.int64)
+        lib.check(lib.litho_source_build(pn, si, so, 0.0, 0.0, cnt, rot, out.ctypes.data, None))
+        ref = O.light_source_annular(si, so, pn) if cnt == 0 else O.light_source_quasar(si, so, pn, cnt, rot)
+        assert (out == ref).all()
+    # pupil: coefficients after the reference's in-place defocus rescale (fp16 values)
+    _, ab = O.wavefront_error(wl.ABERR_FULL, 64, 0.7, 193.0)
+    arr = (C.c_float * len(ab))(*[float(v) for v in ab])
+    pup = np.zeros((64, 64), np.complex64)
+    we = np.zeros((64, 64), np.complex64)
+    lib.check(lib.litho_pupil_build(arr, len(ab), 64, pup.ctypes.data, we.ctypes.data, None))
+    assert np.abs(pup - c["pupil"]).max() < 2e-7          # the reference's own pupil tensor
+    we_ref, _ = O.wavefront_error(wl.ABERR_FULL, 64, 0.7, 193.0)
+    assert (we.real == we_ref).all() and not we.imag.any()
+    z = np.load(f"{H.GOLDEN}/cfg1.npz")
+    _, ab = O.wavefront_error([0, 0, 0, 0, 50], 256, 0.7, 193.0)
+    arr = (C.c_float * len(ab))(*[float(v) for v in ab])
+    pup = np.zeros((256, 256), np.complex64)
+    lib.check(lib.litho_pupil_build(arr, len(ab), 256, pup.ctypes.data, None, None))
+    assert np.abs(pup - z["pupil"]).max() < 2e-7
+
+
 def test_emu_rejects_unsupported():
     lib = H.emu_lib()
     with pytest.raises(Exception):
