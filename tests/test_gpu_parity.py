@@ -305,3 +305,50 @@ def test_two_gpu_sharded_image(tmp_path, golden_dir):
     mp.spawn(_dist_worker, args=(2, port, out_path), nprocs=2, join=True)
     z = np.load(f"{golden_dir}/cfg1.npz")
     assert O.rel_l2(np.load(out_path), z["image"]) < H.TOL
+
+
+def test_cfg4_size_single_points_against_oracle(L, dev):
+    """BASELINE cfg4 grid (4096 px, N = 8192, sub-FFT 2048 = radix 32x32x2): two source points against the
+    oracle's float64 field, and the 4094-px output side of the reference's post-processing."""
+    from lithographysimulator_b200.imaging import AbbeEngine
+    cfg = wl.CONFIGS["cfg4"]
+    pn = cfg.pn
+    geom = cfg.geometry()
+    mft = O.fraunhofer(geom, cfg.pixel_size, cfg.wavelength, True, np.complex128).astype(np.complex64)
+    pf, _ = O.pupil_function(cfg.aberrations, pn, cfg.na, cfg.wavelength)
+    eng = AbbeEngine.get(dev)
+    sh = torch.tensor([[300, -700], [-911, 5]], dtype=torch.int32)
+    mft_d, pf_d = _t(mft, dev), _t(pf, dev)
+    raw = eng.abbe_fft(mft_d, pf_d, None, cfg.pixel_size, 4 / pn, cfg.wavelength, shifts=sh, postprocess=False)
+    ref = np.zeros((pn, pn))
+    for d0, d1 in sh.numpy():
+        ref += np.abs(O.calculate_fft_aerial(np.roll(pf, (d0, d1), (0, 1)), mft, pn, 2 * pn)) ** 2
+    assert O.rel_l2(raw.cpu().numpy(), ref) < H.TOL
+    img = eng.abbe_fft(mft_d, pf_d, None, cfg.pixel_size, 4 / pn, cfg.wavelength, shifts=sh)
+    assert tuple(img.shape) == (4094, 4094)
+    eps, _ = O.calculate_epsilon_n(4 / pn, cfg.pixel_size, cfg.wavelength)
+    assert O.rel_l2(img.cpu().numpy(), O.fft_postprocess(ref, pn, eps, dtype=np.float64)) < H.TOL
+    # mask spectrum of this size through the native kernels (N = 8192 transform, sub-FFT 8192)
+    m = L.Mask(torch.from_numpy(geom), cfg.pixel_size, dev)
+    mine = m.fraunhofer(cfg.wavelength, True).cpu().numpy()
+    assert np.linalg.norm(mine - mft) / np.linalg.norm(mft) < H.TOL
+
+
+def test_cfg5_size_fast_equals_generic(L, dev):
+    """BASELINE cfg5 grid (8192 px, N = 16384, sub-FFT 4096 = radix 32x32x4): fast coarse-grid path against the
+    generic fine-grid kernels on one source point (the oracle would need a 4 GB complex128 FFT here)."""
+    from lithographysimulator_b200.imaging import AbbeEngine
+    pn = 8192
+    ab = torch.tensor([0, 0, 0.01, 0, -150, 0.01], dtype=torch.float16, device=dev)
+    pf = L.Pupil(pn, 193.0, 0.7, ab, dev).generatePupilFunction()
+    g = torch.Generator(device="cpu").manual_seed(3)
+    mft = torch.complex(torch.randn((pn, pn), generator=g), torch.randn((pn, pn), generator=g)).to(dev)
+    sh = torch.tensor([[1500, -900]], dtype=torch.int32)
+    eng = AbbeEngine.get(dev)
+    kw = dict(pixelSize=25, deltaK=4 / pn, wavelength=193.0, shifts=sh, postprocess=False)
+    fast = eng.abbe_fft(mft, pf, None, **kw)
+    gen = eng.abbe_fft(mft, pf, None, generic=True, **kw)
+    assert eng.plan_for(pn, 2 * pn, eng.pupil_support(pf), sh.to(dev)).path == 2
+    num = torch.linalg.vector_norm((fast - gen).double())
+    den = torch.linalg.vector_norm(gen.double())
+    assert float(num / den) < H.TOL
