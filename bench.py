@@ -223,9 +223,16 @@ def run_ours(args):
             main.wait_event(fin_done[i % 2])       # image i-2 has left this plane
         inten.zero_()
         eng.accumulate(plan, mft_d, pf_d, shifts_mine, inten, None, args.batch)
-        reduce_fn(inten)
         if args.no_pipeline:
+            reduce_fn(inten)
             state["img"] = eng.finalize(plan, inten, eps)
+            return
+        # one NCCL sum-reduce of the partial planes to a root that rotates with the image index, so the
+        # post-processing of consecutive images is spread over the ranks instead of repeated on all of them
+        root = i % world
+        if world > 1:
+            dist.reduce(inten, dst=root)
+        if rank != root:
             return
         ready = torch.cuda.Event()
         ready.record(main)
@@ -400,8 +407,9 @@ def run_ours(args):
                 "config": {"workload": f"{cfg.name}: {pn}^2 {cfg.mask} mask, {cfg.source} source {n_src} pts, N={N}, "
                                        "Zernike-aberrated pupil, FFT-approximation solver",
                            "l2": "flushed (256 MB write) between images, inside the timed region", "batch": batch,
-                           "pipeline": "sequential" if args.no_pipeline else
-                           "reduce+post-processing of image i overlap the accumulation of image i+1 (2 streams)",
+                           "pipeline": "sequential, all-reduce, every rank post-processes" if args.no_pipeline else
+                           "post-processing of image i overlaps the accumulation of image i+1 (2 streams); with N>1 "
+                           "the partial planes are sum-reduced to rank i mod N, which alone post-processes image i",
                            "subfft": plan.M, "residues": plan.R,
                            "path": "fast coarse-grid (2 FFTs of length M per line, spectral interpolation once per image)"
                            if plan.path == 2 else "generic fine-grid", "sharding": f"source points interleaved over {world} rank(s), "
