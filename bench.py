@@ -212,6 +212,7 @@ def run_ours(args):
     fin_stream = torch.cuda.Stream(dev)
     planes = [eng.intensity_plane(plan) for _ in range(2)]
     fin_done = [None, None]
+    reduce_work = [None, None]
     state = {"i": 0, "img": None}
 
     def one_image():
@@ -219,6 +220,8 @@ def run_ours(args):
         state["i"] += 1
         inten = planes[i % 2]
         main = torch.cuda.current_stream(dev)
+        if reduce_work[i % 2] is not None:
+            reduce_work[i % 2].wait()              # the reduce of image i-2 has read this plane
         if fin_done[i % 2] is not None:
             main.wait_event(fin_done[i % 2])       # image i-2 has left this plane
         inten.zero_()
@@ -230,20 +233,29 @@ def run_ours(args):
         # one NCCL sum-reduce of the partial planes to a root that rotates with the image index, so the
         # post-processing of consecutive images is spread over the ranks instead of repeated on all of them
         root = i % world
+        work = None
         if world > 1:
-            dist.reduce(inten, dst=root)
+            # asynchronous: the main stream goes straight on to the next image; only the post-processing
+            # stream (and the later reuse of this plane) waits for the reduce
+            work = dist.reduce(inten, dst=root, async_op=True)
+        reduce_work[i % 2] = work
         if rank != root:
             return
         ready = torch.cuda.Event()
         ready.record(main)
         with torch.cuda.stream(fin_stream):
             fin_stream.wait_event(ready)
+            if work is not None:
+                work.wait()                         # fin_stream waits for the NCCL reduce
             state["img"] = eng.finalize(plan, inten, eps)
             done = torch.cuda.Event()
             done.record(fin_stream)
             fin_done[i % 2] = done
 
     def join():
+        for w in reduce_work:
+            if w is not None:
+                w.wait()
         torch.cuda.current_stream(dev).wait_stream(fin_stream)
 
     def barrier():
