@@ -114,18 +114,15 @@ LITHO_HD void rows_body(const RowsParams& P, const Ctx& ctx, cplx* smem) {
                 if (mc >= pn) mc -= pn;
                 return cmul(ldg_c(prow + u), ldg_c(mrow + mc));
             };
-#pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] = zoom_fold<false>(g + TG * e, M, P.plan.L, r, ax, P.twL, ld);
+            zoom_load<16>(v, g, TG, M, P.plan.L, r, ax, P.twL, ld);
         } else if constexpr (KIND == ROW_REAL_PLANE) {
             const float* row = P.real_in + (size_t)line * P.in_pitch;
             auto ld = [&](int u) { return mk(ldg_f(row + u), 0.f); };
-#pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] = zoom_fold<false>(g + TG * e, M, P.plan.L, r, ax, P.twL, ld);
+            zoom_load<16>(v, g, TG, M, P.plan.L, r, ax, P.twL, ld);
         } else {
             const cplx* row = P.cplx_in + (size_t)line * P.in_pitch;
             auto ld = [&](int u) { return ldg_c(row + u); };
-#pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] = zoom_fold<false>(g + TG * e, M, P.plan.L, r, ax, P.twL, ld);
+            zoom_load<16>(v, g, TG, M, P.plan.L, r, ax, P.twL, ld);
         }
     } else {
 #pragma unroll
@@ -176,8 +173,7 @@ LITHO_HD void cols_body(const ColsParams& P, const Ctx& ctx, cplx* smem) {
             const cplx* src = P.T + ((size_t)(sl * P.Rc + rc) * S) * P.Wrc + kkc;
             const int pitch = P.Wrc;
             auto ld = [&](int u) { return ldg_c(src + (size_t)u * pitch); };
-#pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] = zoom_fold<false>(g + TG * e, M, P.plan.L, rr, ax, P.twL, ld);
+            zoom_load<16>(v, g, TG, M, P.plan.L, rr, ax, P.twL, ld);
         } else {
 #pragma unroll
             for (int e = 0; e < 16; ++e) v[e] = mk(0.f, 0.f);

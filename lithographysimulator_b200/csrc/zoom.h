@@ -89,4 +89,43 @@ LITHO_HD cplx zoom_fold(int slot, int M, int L, int r, const AxisIn& ax, const c
     return acc;
 }
 
+// Loads the PPT folded, pre-twiddled inputs of one thread (slots g + TG*e).  When the window does not
+// wrap and S <= M+1 (every slot has at most one input, plus the rim input that shares slot of u = 0)
+// the loads are issued branch-free and up front, so they are all in flight together; otherwise the
+// general two-segment fold is used slot by slot.
+template <int PPT, class LoadFn>
+LITHO_HD void zoom_load(cplx (&v)[PPT], int g, int TG, int M, int L, int r, const AxisIn& ax, const cplx* twL,
+                        LoadFn ld) {
+    const int f = imod(ax.first, ax.period);
+    const bool simple = (ax.S >= 1) && (f + ax.S <= ax.period) && (ax.S <= M + 1);
+    if (simple) {
+        const int base = f - ax.center;  // c'(u) = base + u
+        const int last = (ax.S < M ? ax.S : M) - 1;
+#pragma unroll
+        for (int e = 0; e < PPT; ++e) {
+            const int u = (g + TG * e - base) & (M - 1);
+            v[e] = ld(u <= last ? u : last);
+        }
+#pragma unroll
+        for (int e = 0; e < PPT; ++e) {
+            const int u = (g + TG * e - base) & (M - 1);
+            cplx x = v[e];
+            if (r != 0) x = cmul(x, ldg_c(twL + ((r * (base + u)) & (L - 1))));
+            v[e] = mk(u <= last ? x.x : 0.f, u <= last ? x.y : 0.f);
+        }
+        if (ax.S > M) {  // rim input u = M folds onto the slot of u = 0
+            cplx y = ld(M);
+            if (r != 0) y = cmul(y, ldg_c(twL + ((r * (base + M)) & (L - 1))));
+#pragma unroll
+            for (int e = 0; e < PPT; ++e) {
+                const bool hit = ((g + TG * e - base) & (M - 1)) == 0;
+                v[e] = mk(v[e].x + (hit ? y.x : 0.f), v[e].y + (hit ? y.y : 0.f));
+            }
+        }
+        return;
+    }
+#pragma unroll
+    for (int e = 0; e < PPT; ++e) v[e] = zoom_fold<false>(g + TG * e, M, L, r, ax, twL, ld);
+}
+
 }  // namespace litho
