@@ -106,13 +106,103 @@ LITHO_HD void fast_load_tables(const cplx* tables, cplx* tab, const Ctx& ctx) {
     ctx.sync();
 }
 
+// Inputs of one row FFT: G_s[line][u] = pupil * shifted mask spectrum, pre-twiddled for residue r and with
+// the rim input folded onto slot 0.  Branch-free loads (index clamped, value masked afterwards) so that all
+// loads of a half are in flight together instead of one load-use round trip per element.
+template <int M, int PPT>
+LITHO_HD void fast_row_load(cplx (&v)[PPT], const FastRowsParams& P, int s, int line, int r, int g, const cplx* tab) {
+    using F = FastShape<M, PPT>;
+    constexpr int TG = F::TG;
+    constexpr int H = PPT / 2;
+    const int2_ sh = P.shifts[s];
+    const cplx* prow = P.pupil + (size_t)(P.pr0 + line) * P.pn + P.pc0;
+    // shifts are inside the plan's no-wrap range by contract; clamping keeps a violated contract
+    // memory-safe (the result is then wrong, never out of bounds)
+    const int mr = iclamp(P.pr0 + line + sh.x, 0, P.pn - 1);
+    const int mc = iclamp(P.pc0 + sh.y, 0, P.pn - P.Sc);
+    const cplx* mrow = P.mask + (size_t)mr * P.pn + mc;
+    const int last = P.Sc - 1;
+    const cplx* pg = prow + g;
+    const cplx* mg = mrow + g;
+    if (last >= M - 1) {  // common case: every slot has an input
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            cplx a[H], b[H];
+#pragma unroll
+            for (int i = 0; i < H; ++i) {
+                a[i] = ldg_c(pg + TG * (H * h + i));
+                b[i] = ldg_c(mg + TG * (H * h + i));
+            }
+#pragma unroll
+            for (int i = 0; i < H; ++i) v[H * h + i] = cmul(a[i], b[i]);
+        }
+    } else {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            cplx a[H], b[H];
+#pragma unroll
+            for (int i = 0; i < H; ++i) {
+                const int u = g + TG * (H * h + i);
+                const int uc = u < last ? u : last;
+                a[i] = ldg_c(prow + uc);
+                b[i] = ldg_c(mrow + uc);
+            }
+#pragma unroll
+            for (int i = 0; i < H; ++i) {
+                const int u = g + TG * (H * h + i);
+                const cplx x = cmul(a[i], b[i]);
+                v[H * h + i] = mk(u <= last ? x.x : 0.f, u <= last ? x.y : 0.f);
+            }
+        }
+    }
+    if (r) {
+#pragma unroll
+        for (int e = 0; e < PPT; ++e) v[e] = cmul(v[e], tab[F::PRE_OFF + g + TG * e]);
+    }
+    if (P.Sc > M) {  // rim input u = M folds onto slot 0 with w_2M^(r*M) = (-1)^r
+        const cplx y = cmul(ldg_c(prow + M), ldg_c(mrow + M));
+        const float sgn = (g == 0) ? (r ? -1.f : 1.f) : 0.f;
+        v[0] = mk(v[0].x + sgn * y.x, v[0].y + sgn * y.y);
+    }
+}
+
+// Inputs of one column FFT: T[u][kc] for the thread's slots u = g + TG*e (column kc = src offset).
+// CG selects L2-coherent loads (T written by other CTAs of the same launch, fused kernel).
+template <int M, int PPT, bool CG>
+LITHO_HD void fast_col_load(cplx (&v)[PPT], const cplx* src, int Sr, int rr, int g, const cplx* tab) {
+    using F = FastShape<M, PPT>;
+    constexpr int TG = F::TG;
+    const int last = Sr - 1;
+    const cplx* srcg = src + (size_t)g * M;
+    if (last >= M - 1) {  // common case Sr >= M: every slot has an input, no masking needed
+#pragma unroll
+        for (int e = 0; e < PPT; ++e) v[e] = CG ? ldcg_c(srcg + (size_t)e * (TG * M)) : ldg_c(srcg + (size_t)e * (TG * M));
+    } else {
+#pragma unroll
+        for (int e = 0; e < PPT; ++e) {
+            const int u = g + TG * e;
+            const cplx* pa = (u <= last) ? srcg + (size_t)e * (TG * M) : src + (size_t)last * M;
+            const cplx x = CG ? ldcg_c(pa) : ldg_c(pa);
+            v[e] = mk(u <= last ? x.x : 0.f, u <= last ? x.y : 0.f);
+        }
+    }
+    if (rr) {
+#pragma unroll
+        for (int e = 0; e < PPT; ++e) v[e] = cmul(v[e], tab[F::PRE_OFF + g + TG * e]);
+    }
+    if (Sr > M) {
+        const cplx y = CG ? ldcg_c(src + (size_t)M * M) : ldg_c(src + (size_t)M * M);
+        const float sgn = (g == 0) ? (rr ? -1.f : 1.f) : 0.f;
+        v[0] = mk(v[0].x + sgn * y.x, v[0].y + sgn * y.y);
+    }
+}
+
 // grid.x = any (persistent over the batch*Sr*2 work items), block = ROW_THREADS
 template <int M, int PPT, class Ctx>
 LITHO_HD void fast_rows_body(const FastRowsParams& P, const Ctx& ctx, cplx* smem) {
     using F = FastShape<M, PPT>;
     using Sh = typename F::Sh;
     constexpr int TG = F::TG;
-    constexpr int H = PPT / 2;
     cplx* tab = smem;
     fast_load_tables<M, PPT>(P.tables, tab, ctx);
     const int grp = ctx.tid() / TG;
@@ -133,58 +223,7 @@ LITHO_HD void fast_rows_body(const FastRowsParams& P, const Ctx& ctx, cplx* smem
         const int line = active ? li - sl * P.Sr : 0;
         cplx v[PPT];
         if (active) {
-            const int2_ sh = P.shifts[P.s_begin + sl];
-            const cplx* prow = P.pupil + (size_t)(P.pr0 + line) * P.pn + P.pc0;
-            // shifts are inside the plan's no-wrap range by contract; clamping keeps a violated
-            // contract memory-safe (the result is then wrong, never out of bounds)
-            const int mr = iclamp(P.pr0 + line + sh.x, 0, P.pn - 1);
-            const int mc = iclamp(P.pc0 + sh.y, 0, P.pn - P.Sc);
-            const cplx* mrow = P.mask + (size_t)mr * P.pn + mc;
-            // Branch-free loads (index clamped, value masked afterwards) so that all loads of a half are
-            // in flight together instead of one load-use round trip per element.
-            const int last = P.Sc - 1;
-            const cplx* pg = prow + g;
-            const cplx* mg = mrow + g;
-            if (last >= M - 1) {  // common case: every slot has an input
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    cplx a[H], b[H];
-#pragma unroll
-                    for (int i = 0; i < H; ++i) {
-                        a[i] = ldg_c(pg + TG * (H * h + i));
-                        b[i] = ldg_c(mg + TG * (H * h + i));
-                    }
-#pragma unroll
-                    for (int i = 0; i < H; ++i) v[H * h + i] = cmul(a[i], b[i]);
-                }
-            } else {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    cplx a[H], b[H];
-#pragma unroll
-                    for (int i = 0; i < H; ++i) {
-                        const int u = g + TG * (H * h + i);
-                        const int uc = u < last ? u : last;
-                        a[i] = ldg_c(prow + uc);
-                        b[i] = ldg_c(mrow + uc);
-                    }
-#pragma unroll
-                    for (int i = 0; i < H; ++i) {
-                        const int u = g + TG * (H * h + i);
-                        const cplx x = cmul(a[i], b[i]);
-                        v[H * h + i] = mk(u <= last ? x.x : 0.f, u <= last ? x.y : 0.f);
-                    }
-                }
-            }
-            if (r) {
-#pragma unroll
-                for (int e = 0; e < PPT; ++e) v[e] = cmul(v[e], tab[F::PRE_OFF + g + TG * e]);
-            }
-            if (P.Sc > M) {  // rim input u = M folds onto slot 0 with w_2M^(r*M) = (-1)^r
-                const cplx y = cmul(ldg_c(prow + M), ldg_c(mrow + M));
-                const float sgn = (g == 0) ? (r ? -1.f : 1.f) : 0.f;
-                v[0] = mk(v[0].x + sgn * y.x, v[0].y + sgn * y.y);
-            }
+            fast_row_load<M, PPT>(v, P, P.s_begin + sl, line, r, g, tab);
         } else {
 #pragma unroll
             for (int e = 0; e < PPT; ++e) v[e] = mk(0.f, 0.f);
@@ -223,31 +262,7 @@ LITHO_HD void fast_cols_body(const FastColsParams& P, const Ctx& ctx, cplx* smem
     for (int sl = 0; sl < P.batch; ++sl) {
         const cplx* src = P.T + ((size_t)(sl * 2 + rc) * P.Sr) * M + kc;
         cplx v[PPT];
-        const int last = P.Sr - 1;
-        const cplx* srcg = src + (size_t)g * M;
-        // Branch-free loads so that all of them are in flight together (one load-use round trip per
-        // FFT, not per element).  Common case Sr >= M: every slot has an input, no masking needed.
-        if (last >= M - 1) {
-#pragma unroll
-            for (int e = 0; e < PPT; ++e) v[e] = ldg_c(srcg + (size_t)e * (TG * M));
-        } else {
-#pragma unroll
-            for (int e = 0; e < PPT; ++e) {
-                const int u = g + TG * e;
-                const cplx* pa = (u <= last) ? srcg + (size_t)e * (TG * M) : src + (size_t)last * M;
-                const cplx x = ldg_c(pa);
-                v[e] = mk(u <= last ? x.x : 0.f, u <= last ? x.y : 0.f);
-            }
-        }
-        if (rr) {
-#pragma unroll
-            for (int e = 0; e < PPT; ++e) v[e] = cmul(v[e], tab[F::PRE_OFF + g + TG * e]);
-        }
-        if (P.Sr > M) {
-            const cplx y = ldg_c(src + (size_t)M * M);
-            const float sgn = (g == 0) ? (rr ? -1.f : 1.f) : 0.f;
-            v[0] = mk(v[0].x + sgn * y.x, v[0].y + sgn * y.y);
-        }
+        fast_col_load<M, PPT, false>(v, src, P.Sr, rr, g, tab);
         fft_run<M, PPT, false>(v, ex, CB, g, tw, gs);
         const float w = P.weights ? P.weights[P.s_begin + sl] : 1.f;
 #pragma unroll
@@ -256,6 +271,164 @@ LITHO_HD void fast_cols_body(const FastColsParams& P, const Ctx& ctx, cplx* smem
     float* dst = P.ic + ((size_t)(rr * 2 + rc) * M + g) * M + kc;
 #pragma unroll
     for (int e = 0; e < PPT; ++e) dst[(size_t)(TG * e) * M] += acc[e];
+}
+
+// ----------------------------------------------------------------------------- fused persistent kernel
+// One launch per image: persistent CTAs pull work items from a global queue that interleaves the row
+// pass of source-point group k+1 with the column pass of group k.  T lives in a small ring of slots that
+// stays L2-resident (no HBM round trip, no launch gaps, no partial waves except at the very end, twiddle
+// tables loaded once per CTA).  Dependencies are device-scope counters:
+//   rows_done[k]  : column items of group k wait until every row item of group k has been stored;
+//   cols_done[k]  : row items of group k+NS wait until the ring slot has been consumed;
+//   tile_ver[t]   : the read-modify-write of an intensity tile is ordered across groups (deterministic sums).
+// Every item only waits on items that precede it in the queue, and items are handed out in queue order
+// to running CTAs, so the scheme cannot deadlock whatever the number of resident CTAs.
+struct FusedParams {
+    FastRowsParams r;      // pupil, mask, window, shifts, tables; r.T = ring base
+    const float* weights;
+    float* ic;
+    int n_src, B, NS;      // source points, points per group, ring slots (in groups)
+    int G, nRf, nRl, nC;   // groups, row items of a full / the last group, column items per group
+    int* ctr;              // [0] next item, [1..G] rows_done, [1+G..2G] cols_done, [1+2G..] tile_ver[nC]
+    int* err;              // set to 1 if a wait timed out (results are then invalid)
+};
+
+template <class Ctx>
+LITHO_HD void fused_wait(const int* p, int target, int* err, const Ctx& ctx) {
+    if (ctx.tid() == 0) {
+        long spins = 0;
+        while (ld_volatile_i(p) < target) {
+            backoff();
+            if (++spins > 20000000L) {  // ~4 s: never hang the GPU on a logic error
+                *err = 1;
+                break;
+            }
+        }
+        fence_gpu();
+    }
+    ctx.sync();
+}
+
+template <int M, class Ctx>
+LITHO_HD void fast_fused_body(const FusedParams& P, const Ctx& ctx, cplx* smem, int* s_item) {
+    constexpr int PPT = 32;
+    using F = FastShape<M, PPT>;
+    using Sh = typename F::Sh;
+    constexpr int TG = F::TG;
+    constexpr int CB = F::CB;
+    static_assert(F::ROW_THREADS == 256 && F::COL_THREADS == 256, "fused kernel needs 256-thread row and column shapes");
+    constexpr int NBLK = M / CB;
+    cplx* tab = smem;
+    fast_load_tables<M, PPT>(P.r.tables, tab, ctx);
+    cplx* exbase = smem + F::NTAB_PAD;
+    const SmemTw<M, PPT> tw{tab};
+    const int tid = ctx.tid();
+    // row-role indices
+    const int grp = tid / TG, gr = tid - grp * TG;
+    // column-role indices
+    const int col = tid % CB, gc = tid / CB;
+    int* rows_done = P.ctr + 1;
+    int* cols_done = P.ctr + 1 + P.G;
+    int* tile_ver = P.ctr + 1 + 2 * P.G;
+    const size_t slot_elems = (size_t)P.B * 2 * P.r.Sr * M;
+    const int nfull = P.G >= 2 ? P.G - 2 : 0;       // blocks [R(k+1) full, C(k)]
+    const int bs = P.nRf + P.nC;
+    const int nR0 = P.G >= 2 ? P.nRf : P.nRl;
+    const long total = (long)nR0 + (long)nfull * bs + (P.G >= 2 ? (long)P.nRl + P.nC : 0) + P.nC;
+
+    for (;;) {
+        if (tid == 0) *s_item = atomic_add_i(P.ctr, 1);
+        ctx.sync();
+        long i = *s_item;
+        ctx.sync();
+        if (i >= total) break;
+        // ---- decode queue position -> (is_row, group k, index within the pass) ----
+        bool is_row;
+        int k, idx;
+        if (i < nR0) { is_row = true; k = 0; idx = (int)i; }
+        else {
+            i -= nR0;
+            if (i < (long)nfull * bs) {
+                k = (int)(i / bs);
+                const int o = (int)(i - (long)k * bs);
+                if (o < P.nRf) { is_row = true; k += 1; idx = o; }
+                else { is_row = false; idx = o - P.nRf; }
+            } else {
+                i -= (long)nfull * bs;
+                if (P.G >= 2 && i < P.nRl) { is_row = true; k = P.G - 1; idx = (int)i; }
+                else {
+                    if (P.G >= 2) i -= P.nRl;
+                    is_row = false;
+                    if (P.G >= 2 && i < P.nC) { k = P.G - 2; idx = (int)i; }
+                    else { k = P.G - 1; idx = (int)(P.G >= 2 ? i - P.nC : i); }
+                }
+            }
+        }
+        const int s0 = k * P.B;
+        const int Bk = (P.n_src - s0) < P.B ? (P.n_src - s0) : P.B;
+        cplx* Tslot = P.r.T + (size_t)(k % P.NS) * slot_elems;
+
+        if (is_row) {
+            if (k >= P.NS) fused_wait(cols_done + (k - P.NS), P.nC, P.err, ctx);  // ring slot consumed
+            const int item = idx * F::ROW_GROUPS + grp;
+            const bool active = item < Bk * P.r.Sr * 2;
+            const int r = item & 1;
+            const int li = item >> 1;
+            const int sl = active ? li / P.r.Sr : 0;
+            const int line = active ? li - sl * P.r.Sr : 0;
+            cplx v[PPT];
+            if (active) {
+                fast_row_load<M, PPT>(v, P.r, s0 + sl, line, r, gr, tab);
+            } else {
+#pragma unroll
+                for (int e = 0; e < PPT; ++e) v[e] = mk(0.f, 0.f);
+            }
+            const GroupSync<Ctx, F::ROW_SYNC> gs{ctx, 1 + grp, TG};
+            fft_run<M, PPT, false>(v, exbase + grp * Sh::SMEM_ELEMS, 1, gr, tw, gs);
+            if (active) {
+                cplx* dst = Tslot + ((size_t)(sl * 2 + r) * P.r.Sr + line) * M + gr;
+#pragma unroll
+                for (int e = 0; e < PPT; ++e) dst[TG * e] = v[e];
+            }
+            ctx.sync();
+            if (tid == 0) {
+                fence_gpu();
+                atomic_add_i(rows_done + k, 1);
+            }
+        } else {
+            const int nRk = (k == P.G - 1) ? P.nRl : P.nRf;
+            fused_wait(rows_done + k, nRk, P.err, ctx);   // every row of this group is in T
+            fused_wait(tile_ver + idx, k, P.err, ctx);    // previous groups have updated this tile
+            const int rr = idx / (2 * NBLK);
+            const int rc = (idx / NBLK) & 1;
+            const int kc = (idx % NBLK) * CB + col;
+            const GroupSync<Ctx, 2> gs{ctx, 0, 0};
+            float acc[PPT];
+#pragma unroll
+            for (int e = 0; e < PPT; ++e) acc[e] = 0.f;
+            for (int sl = 0; sl < Bk; ++sl) {
+                const cplx* src = Tslot + ((size_t)(sl * 2 + rc) * P.r.Sr) * M + kc;
+                cplx v[PPT];
+                fast_col_load<M, PPT, true>(v, src, P.r.Sr, rr, gc, tab);
+                fft_run<M, PPT, false>(v, exbase + col, CB, gc, tw, gs);
+                const float w = P.weights ? P.weights[s0 + sl] : 1.f;
+#pragma unroll
+                for (int e = 0; e < PPT; ++e) acc[e] += w * cnorm2(v[e]);
+            }
+            float* dst = P.ic + ((size_t)(rr * 2 + rc) * M + gc) * M + kc;
+#pragma unroll
+            for (int e = 0; e < PPT; ++e) {
+                float* q = dst + (size_t)(TG * e) * M;
+                stcg_f(q, ldcg_f(q) + acc[e]);
+            }
+            ctx.sync();
+            if (tid == 0) {
+                fence_gpu();
+                atomic_add_i(tile_ver + idx, 1);
+                atomic_add_i(cols_done + k, 1);
+            }
+        }
+    }
 }
 
 // ----------------------------------------------------------------------------- rim lines

@@ -55,6 +55,57 @@ LITHO_HD float ldg_f(const float* p) {
 #endif
 }
 
+// L2-coherent (cache-global) accesses for data produced by other CTAs of the same launch
+LITHO_HD cplx ldcg_c(const cplx* p) {
+#if defined(__CUDA_ARCH__)
+    float2 v = __ldcg(reinterpret_cast<const float2*>(p));
+    return mk(v.x, v.y);
+#else
+    return *p;
+#endif
+}
+LITHO_HD float ldcg_f(const float* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldcg(p);
+#else
+    return *p;
+#endif
+}
+LITHO_HD void stcg_f(float* p, float v) {
+#if defined(__CUDA_ARCH__)
+    __stcg(p, v);
+#else
+    *p = v;
+#endif
+}
+// device-scope counters used by the fused persistent kernel
+LITHO_HD int atomic_add_i(int* p, int v) {
+#if defined(__CUDA_ARCH__)
+    return atomicAdd(p, v);
+#else
+    int o = *p;
+    *p += v;
+    return o;
+#endif
+}
+LITHO_HD int ld_volatile_i(const int* p) {
+#if defined(__CUDA_ARCH__)
+    return *reinterpret_cast<const volatile int*>(p);
+#else
+    return *p;
+#endif
+}
+LITHO_HD void fence_gpu() {
+#if defined(__CUDA_ARCH__)
+    __threadfence();
+#endif
+}
+LITHO_HD void backoff() {
+#if defined(__CUDA_ARCH__)
+    __nanosleep(200);
+#endif
+}
+
 // floor-mod for a possibly negative a, b > 0
 LITHO_HD int imod(int a, int b) {
     int m = a % b;

@@ -287,6 +287,10 @@ struct litho_plan {
     int ext[8];      // non-zero extents of the first/last window row and column (window coordinates)
     cplx* tables;    // device twiddle tables of the fast kernels (owned by the plan)
     int n_sm;
+    int fused;       // 1: one persistent launch per accumulate call (fast_fused_body)
+    int fused_B;     // source points per group of the fused kernel
+    int* counters;   // device: work-queue index, dependency counters, error flag (owned by the plan)
+    int counters_cap;
 #if !defined(LITHO_EMU)
     cudaStream_t aux_stream;  // row passes of the fast path run here, overlapping the column passes
     cudaEvent_t ev_start, ev_rows[LITHO_TSLOTS], ev_cols[LITHO_TSLOTS];
@@ -307,6 +311,14 @@ static int dispatch_fast_cols(int M, int ppt, const FastColsParams& P, litho_str
     switch (M) {
 #define X(m) case m: return ppt == 16 ? launch_fast_cols_m<m, 16>(P, st) : launch_fast_cols_m<m, 32>(P, st);
         LITHO_FOR_EACH_FAST_M(X)
+#undef X
+    }
+    return -1;
+}
+static int dispatch_fast_fused(int M, const FusedParams& P, int gx, litho_stream_t st) {
+    switch (M) {
+#define X(m) case m: return launch_fast_fused_m<m>(P, gx, st);
+        LITHO_FOR_EACH_FUSED_M(X)
 #undef X
     }
     return -1;
@@ -520,6 +532,7 @@ int litho_plan_create_ex(int pn, int N, const int* bbox, int flags, litho_plan_t
     size_t per = (size_t)p->zp.R * p->Sr * p->zp.Wr * sizeof(cplx);
     // ---- fast path eligibility: even window fit S <= Mf+1, coarse grid Nc = 2*Mf no finer than N ----
     p->path = 1; p->tables = nullptr; p->Mf = p->Nc = p->q = 0; p->rim_row = p->rim_col = 0;
+    p->fused = 0; p->fused_B = 2; p->counters = nullptr; p->counters_cap = 0;
 #if !defined(LITHO_EMU)
     p->aux_stream = nullptr;
 #endif
@@ -572,6 +585,22 @@ int litho_plan_create_ex(int pn, int N, const int* bbox, int flags, litho_plan_t
             }
         }
 #endif
+        // fused persistent kernel: available for 512 <= M <= 2048 with 32 points per thread
+        p->fused = (p->ppt == 32 && Mf >= 512 && Mf <= 2048) ? 1 : 0;
+        if (const char* env = getenv("LITHO_FUSED")) p->fused = p->fused && atoi(env) != 0;
+        if (const char* env = getenv("LITHO_FUSED_B")) {
+            const int v = atoi(env);
+            if (v >= 1 && v <= 16) p->fused_B = v;
+        }
+        if (p->fused) {
+            p->counters_cap = 1 + 2 * 65536 + 4 * Mf + 8;
+            rc = be_malloc((void**)&p->counters, sizeof(int) * p->counters_cap);
+            if (rc != 0) {
+                be_free(p->tables);
+                delete p;
+                return fail(LITHO_ERR_CUDA, std::string("plan_create: counters: ") + be_errstr(rc));
+            }
+        }
         p->path = 2; p->Mf = Mf; p->Nc = 2 * Mf; p->q = N / (2 * Mf);
         p->rim_row = (p->Sr == Mf + 1);
         p->rim_col = (p->Sc == Mf + 1);
@@ -598,6 +627,7 @@ int litho_plan_create_ex(int pn, int N, const int* bbox, int flags, litho_plan_t
 void litho_plan_destroy(litho_plan_t* p) {
     if (!p) return;
     if (p->tables) be_free(p->tables);
+    if (p->counters) be_free(p->counters);
 #if !defined(LITHO_EMU)
     if (p->aux_stream) {
         cudaStreamSynchronize(p->aux_stream);
@@ -736,6 +766,40 @@ int litho_abbe_fft_accumulate_ex(const litho_plan_t* p, const void* maskFT, cons
         memset(&fc, 0, sizeof(fc));
         fc.T = (const cplx*)workspace; fc.Sr = p->Sr; fc.weights = weights; fc.tables = p->tables;
         fc.ic = intensity;
+        if (p->fused && phases == 3) {
+            // one persistent launch per chunk of <= 65536 groups (counter capacity)
+            const int B = p->fused_B;
+            const size_t group_bytes = (size_t)B * 2 * p->Sr * p->Mf * sizeof(cplx);
+            int NS = (int)(workspace_bytes / group_bytes);
+            if (NS > 4) NS = 4;  // keep the ring L2-resident
+            if (NS < 2) return fail(LITHO_ERR_WORKSPACE, "accumulate: workspace too small for the fused ring");
+            const int nC = 4 * (p->Mf / (256 / (p->Mf / 32)));
+            for (int s0 = 0; s0 < n_src; s0 += 65536 * B) {
+                const int ns = (n_src - s0) < 65536 * B ? (n_src - s0) : 65536 * B;
+                FusedParams fp;
+                memset(&fp, 0, sizeof(fp));
+                fp.r = fr;
+                fp.r.shifts = (const int2_*)shifts + s0;
+                fp.weights = weights ? weights + s0 : nullptr;
+                fp.ic = intensity;
+                fp.n_src = ns; fp.B = B; fp.NS = NS;
+                fp.G = (ns + B - 1) / B;
+                const int Bl = ns - (fp.G - 1) * B;
+                const int groups_per_item = 256 / (p->Mf / 32);
+                fp.nRf = (B * p->Sr * 2 + groups_per_item - 1) / groups_per_item;
+                fp.nRl = (Bl * p->Sr * 2 + groups_per_item - 1) / groups_per_item;
+                fp.nC = nC;
+                const int n_ctr = 1 + 2 * fp.G + nC;
+                fp.ctr = p->counters;
+                fp.err = p->counters + p->counters_cap - 1;
+#if defined(LITHO_EMU)
+                memset(p->counters, 0, sizeof(int) * n_ctr);
+#else
+                BE_CHECK((int)cudaMemsetAsync(p->counters, 0, sizeof(int) * n_ctr, st));
+#endif
+                BE_CHECK(dispatch_fast_fused(p->Mf, fp, p->n_sm * 2, st));
+            }
+        } else {
         // T is double-buffered: the row pass of batch b+1 runs on the plan's auxiliary stream while the
         // column pass of batch b runs on the caller's stream, so the tail of one kernel overlaps the head
         // of the other (both are short, ~20-40 us at cfg3).  rows(b) -> cols(b) and cols(b) -> rows(b+LITHO_TSLOTS)
@@ -771,6 +835,7 @@ int litho_abbe_fft_accumulate_ex(const litho_plan_t* p, const void* maskFT, cons
 #endif
             if (phases & 1) BE_CHECK(dispatch_fast_rows(p->Mf, p->ppt, fr, p->n_sm * (p->ppt == 16 ? 4 : 2), st));
             if (phases & 2) BE_CHECK(dispatch_fast_cols(p->Mf, p->ppt, fc, st));
+        }
         }
         if ((phases & 2) && p->q > 1 && (p->rim_row || p->rim_col)) {
             RimParams rm;
