@@ -105,6 +105,18 @@ LITHO_HD void fast_load_tables(const cplx* tables, cplx* tab, const Ctx& ctx) {
     for (int i = ctx.tid(); i < FastShape<M, PPT>::NTAB; i += ctx.bdim()) tab[i] = tables[i];
     ctx.sync();
 }
+// Asynchronous variant: start the copy (16-byte chunks; the device table is padded to NTAB_PAD elements),
+// do other work, then fast_tables_wait() before the first use.
+template <int M, int PPT, class Ctx>
+LITHO_HD void fast_tables_begin(const cplx* tables, cplx* tab, const Ctx& ctx) {
+    for (int i = ctx.tid(); i < FastShape<M, PPT>::NTAB_PAD / 2; i += ctx.bdim())
+        ctx.cp_async16(tab + 2 * i, tables + 2 * i);
+}
+template <class Ctx>
+LITHO_HD void fast_tables_wait(const Ctx& ctx) {
+    ctx.cp_async_wait();
+    ctx.sync();
+}
 
 // Inputs of one row FFT: G_s[line][u] = pupil * shifted mask spectrum, pre-twiddled for residue r and with
 // the rim input folded onto slot 0.  Branch-free loads (index clamped, value masked afterwards) so that all
@@ -169,7 +181,7 @@ LITHO_HD void fast_row_load(cplx (&v)[PPT], const FastRowsParams& P, int s, int 
 // Inputs of one column FFT: T[u][kc] for the thread's slots u = g + TG*e (column kc = src offset).
 // CG selects L2-coherent loads (T written by other CTAs of the same launch, fused kernel).
 template <int M, int PPT, bool CG>
-LITHO_HD void fast_col_load(cplx (&v)[PPT], const cplx* src, int Sr, int rr, int g, const cplx* tab) {
+LITHO_HD void fast_col_load_raw(cplx (&v)[PPT], const cplx* src, int Sr, int g) {
     using F = FastShape<M, PPT>;
     constexpr int TG = F::TG;
     const int last = Sr - 1;
@@ -186,6 +198,12 @@ LITHO_HD void fast_col_load(cplx (&v)[PPT], const cplx* src, int Sr, int rr, int
             v[e] = mk(u <= last ? x.x : 0.f, u <= last ? x.y : 0.f);
         }
     }
+}
+
+template <int M, int PPT, bool CG>
+LITHO_HD void fast_col_finish(cplx (&v)[PPT], const cplx* src, int Sr, int rr, int g, const cplx* tab) {
+    using F = FastShape<M, PPT>;
+    constexpr int TG = F::TG;
     if (rr) {
 #pragma unroll
         for (int e = 0; e < PPT; ++e) v[e] = cmul(v[e], tab[F::PRE_OFF + g + TG * e]);
@@ -195,6 +213,12 @@ LITHO_HD void fast_col_load(cplx (&v)[PPT], const cplx* src, int Sr, int rr, int
         const float sgn = (g == 0) ? (rr ? -1.f : 1.f) : 0.f;
         v[0] = mk(v[0].x + sgn * y.x, v[0].y + sgn * y.y);
     }
+}
+
+template <int M, int PPT, bool CG>
+LITHO_HD void fast_col_load(cplx (&v)[PPT], const cplx* src, int Sr, int rr, int g, const cplx* tab) {
+    fast_col_load_raw<M, PPT, CG>(v, src, Sr, g);
+    fast_col_finish<M, PPT, CG>(v, src, Sr, rr, g, tab);
 }
 
 // grid.x = any (persistent over the batch*Sr*2 work items), block = ROW_THREADS
@@ -244,7 +268,7 @@ LITHO_HD void fast_cols_body(const FastColsParams& P, const Ctx& ctx, cplx* smem
     constexpr int TG = F::TG;
     constexpr int CB = F::CB;
     cplx* tab = smem;
-    fast_load_tables<M, PPT>(P.tables, tab, ctx);
+    fast_tables_begin<M, PPT>(P.tables, tab, ctx);  // lands while the first inputs are in flight
     const int col = ctx.tid() % CB;
     const int g = ctx.tid() / CB;
     cplx* ex = smem + F::NTAB_PAD + col;
@@ -255,22 +279,32 @@ LITHO_HD void fast_cols_body(const FastColsParams& P, const Ctx& ctx, cplx* smem
     const SmemTw<M, PPT> tw{tab};
     const GroupSync<Ctx, 2> gs{ctx, 0, 0};
 
+    // The accumulators start from the current intensity values: the read half of the plane's
+    // read-modify-write is issued here and hidden behind the first FFT instead of stalling the epilogue.
+    float* dst = P.ic + ((size_t)(rr * 2 + rc) * M + g) * M + kc;
     float acc[PPT];
 #pragma unroll
-    for (int e = 0; e < PPT; ++e) acc[e] = 0.f;
+    for (int e = 0; e < PPT; ++e) acc[e] = dst[(size_t)(TG * e) * M];
 
     for (int sl = 0; sl < P.batch; ++sl) {
         const cplx* src = P.T + ((size_t)(sl * 2 + rc) * P.Sr) * M + kc;
         cplx v[PPT];
-        fast_col_load<M, PPT, false>(v, src, P.Sr, rr, g, tab);
+        if (sl == 0) {
+            // raw loads first, tables second: both are in flight together
+            fast_col_load_raw<M, PPT, false>(v, src, P.Sr, g);
+            fast_tables_wait(ctx);
+            fast_col_finish<M, PPT, false>(v, src, P.Sr, rr, g, tab);
+        } else {
+            fast_col_load<M, PPT, false>(v, src, P.Sr, rr, g, tab);
+        }
         fft_run<M, PPT, false>(v, ex, CB, g, tw, gs);
         const float w = P.weights ? P.weights[P.s_begin + sl] : 1.f;
 #pragma unroll
         for (int e = 0; e < PPT; ++e) acc[e] += w * cnorm2(v[e]);
     }
-    float* dst = P.ic + ((size_t)(rr * 2 + rc) * M + g) * M + kc;
+    if (P.batch == 0) fast_tables_wait(ctx);
 #pragma unroll
-    for (int e = 0; e < PPT; ++e) dst[(size_t)(TG * e) * M] += acc[e];
+    for (int e = 0; e < PPT; ++e) dst[(size_t)(TG * e) * M] = acc[e];
 }
 
 // ----------------------------------------------------------------------------- fused persistent kernel
@@ -403,9 +437,10 @@ LITHO_HD void fast_fused_body(const FusedParams& P, const Ctx& ctx, cplx* smem, 
             const int rc = (idx / NBLK) & 1;
             const int kc = (idx % NBLK) * CB + col;
             const GroupSync<Ctx, 2> gs{ctx, 0, 0};
+            float* dst = P.ic + ((size_t)(rr * 2 + rc) * M + gc) * M + kc;
             float acc[PPT];
 #pragma unroll
-            for (int e = 0; e < PPT; ++e) acc[e] = 0.f;
+            for (int e = 0; e < PPT; ++e) acc[e] = ldcg_f(dst + (size_t)(TG * e) * M);
             for (int sl = 0; sl < Bk; ++sl) {
                 const cplx* src = Tslot + ((size_t)(sl * 2 + rc) * P.r.Sr) * M + kc;
                 cplx v[PPT];
@@ -415,12 +450,8 @@ LITHO_HD void fast_fused_body(const FusedParams& P, const Ctx& ctx, cplx* smem, 
 #pragma unroll
                 for (int e = 0; e < PPT; ++e) acc[e] += w * cnorm2(v[e]);
             }
-            float* dst = P.ic + ((size_t)(rr * 2 + rc) * M + gc) * M + kc;
 #pragma unroll
-            for (int e = 0; e < PPT; ++e) {
-                float* q = dst + (size_t)(TG * e) * M;
-                stcg_f(q, ldcg_f(q) + acc[e]);
-            }
+            for (int e = 0; e < PPT; ++e) stcg_f(dst + (size_t)(TG * e) * M, acc[e]);
             ctx.sync();
             if (tid == 0) {
                 fence_gpu();

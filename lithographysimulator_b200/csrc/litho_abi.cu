@@ -350,7 +350,7 @@ static std::vector<cplx> build_fast_tables(int M, int ppt) {
         for (int k = 0; k < NS1; ++k) push((double)tt * k, (double)NS1 * R1);
     for (int tt = 1; tt < R2; ++tt)
         for (int k = 0; k < NS2; ++k) push((double)tt * k, (double)NS2 * R2);
-    return t;
+    return t;  // NTAB entries; the device copy is padded to an even count for 16-byte chunk copies
 }
 
 static int dispatch_shape(int M, int* fpc, int* cb) {
@@ -556,10 +556,11 @@ int litho_plan_create_ex(int pn, int N, const int* bbox, int flags, litho_plan_t
             if (atoi(env) == 32) p->ppt = 32;
         }
         std::vector<cplx> tab = build_fast_tables(Mf, p->ppt);
-        if ((int)tab.size() != dispatch_fast_ntab(Mf, p->ppt)) {
+        if ((int)tab.size() != dispatch_fast_ntab(Mf, p->ppt)) {  // (checked before the padding entry is added)
             delete p;
             return fail(LITHO_ERR_ARG, "plan_create: internal table layout mismatch");
         }
+        tab.push_back(mk(0.f, 0.f));  // padding (NTAB_PAD)
         rc = be_malloc((void**)&p->tables, tab.size() * sizeof(cplx));
         if (rc == 0) rc = be_h2d(p->tables, tab.data(), tab.size() * sizeof(cplx), 0);
 #if !defined(LITHO_EMU)
@@ -586,8 +587,9 @@ int litho_plan_create_ex(int pn, int N, const int* bbox, int flags, litho_plan_t
         }
 #endif
         // fused persistent kernel: available for 512 <= M <= 2048 with 32 points per thread
-        p->fused = (p->ppt == 32 && Mf >= 512 && Mf <= 2048) ? 1 : 0;
-        if (const char* env = getenv("LITHO_FUSED")) p->fused = p->fused && atoi(env) != 0;
+        // (measured slower than the two-kernel pipeline at cfg3, profiles/README.md: off unless LITHO_FUSED=1)
+        p->fused = 0;
+        if (const char* env = getenv("LITHO_FUSED")) p->fused = (atoi(env) != 0 && p->ppt == 32 && Mf >= 512 && Mf <= 2048);
         if (const char* env = getenv("LITHO_FUSED_B")) {
             const int v = atoi(env);
             if (v >= 1 && v <= 16) p->fused_B = v;
@@ -766,13 +768,15 @@ int litho_abbe_fft_accumulate_ex(const litho_plan_t* p, const void* maskFT, cons
         memset(&fc, 0, sizeof(fc));
         fc.T = (const cplx*)workspace; fc.Sr = p->Sr; fc.weights = weights; fc.tables = p->tables;
         fc.ic = intensity;
-        if (p->fused && phases == 3) {
+        const bool use_fused = p->fused && phases == 3 &&
+                               workspace_bytes >= 2 * (size_t)p->fused_B * 2 * p->Sr * p->Mf * sizeof(cplx);
+        if (use_fused) {
             // one persistent launch per chunk of <= 65536 groups (counter capacity)
             const int B = p->fused_B;
             const size_t group_bytes = (size_t)B * 2 * p->Sr * p->Mf * sizeof(cplx);
             int NS = (int)(workspace_bytes / group_bytes);
             if (NS > 4) NS = 4;  // keep the ring L2-resident
-            if (NS < 2) return fail(LITHO_ERR_WORKSPACE, "accumulate: workspace too small for the fused ring");
+            if (NS < 2) NS = 0;
             const int nC = 4 * (p->Mf / (256 / (p->Mf / 32)));
             for (int s0 = 0; s0 < n_src; s0 += 65536 * B) {
                 const int ns = (n_src - s0) < 65536 * B ? (n_src - s0) : 65536 * B;

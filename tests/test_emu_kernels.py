@@ -80,6 +80,7 @@ def test_emu_fused_persistent_kernel(monkeypatch):
     """pn = 1024 -> sub-FFT 512: the fused persistent kernel (work queue interleaving the row pass of group
     k+1 with the column pass of group k, ring of T slots, dependency counters).  Three groups of one source
     point exercise every branch of the queue decoder; checked against the oracle."""
+    monkeypatch.setenv("LITHO_FUSED", "1")   # experimental path, off by default
     monkeypatch.setenv("LITHO_FUSED_B", "1")
     pn = 1024
     pf, _ = O.pupil_function([0, 0, 0.01, 0, 40], pn, 0.7, 193.0)
