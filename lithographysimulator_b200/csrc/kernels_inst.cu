@@ -168,6 +168,7 @@ __global__ void __launch_bounds__(256, 2) abbe_fast_fused_kernel(const __grid_co
 #endif
 template <int M>
 int launch_fast_fused_m(const FusedParams& P, int gx, litho_stream_t st) {
+    if (FastShape<M, 32>::COL_THREADS != 256) return -2;  // the fused body needs 256-thread column tiles
 #if defined(LITHO_EMU)
     (void)st;
     litho_emu::launch(gx, 1, 1, 256, FusedSmem<M>::BYTES, [&](const litho_emu::EmuCtx& c, char* s) {

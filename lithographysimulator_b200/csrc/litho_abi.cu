@@ -801,7 +801,9 @@ int litho_abbe_fft_accumulate_ex(const litho_plan_t* p, const void* maskFT, cons
 #else
                 BE_CHECK((int)cudaMemsetAsync(p->counters, 0, sizeof(int) * n_ctr, st));
 #endif
-                BE_CHECK(dispatch_fast_fused(p->Mf, fp, p->n_sm * 2, st));
+                const int frc = dispatch_fast_fused(p->Mf, fp, p->n_sm * 2, st);
+                if (frc == -2) return fail(LITHO_ERR_ARG, "accumulate: fused kernel not built for this column shape (unset LITHO_FUSED)");
+                BE_CHECK(frc);
             }
         } else {
         // T is double-buffered: the row pass of batch b+1 runs on the plan's auxiliary stream while the
