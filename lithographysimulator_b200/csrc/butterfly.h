@@ -21,6 +21,32 @@ LITHO_HD cplx mul_w(cplx a, float cr, float ci) {
     return mk(a.x * cr - a.y * si, a.x * si + a.y * cr);
 }
 
+// Twiddled radix-2 butterfly  (p, m) = e +- w*o,  w = cr + i*s*ci (s = +1 inverse / -1 forward), in
+// 6 FMA-pipe instructions instead of 8: with t = si/cr,  w*o = cr*(o.x - t*o.y, o.y + t*o.x), so two
+// FMAs form the bracket and four more fold the scale into the add/subtract (Linzer-Feig form; the
+// cotangent variant is used when |si| > |cr| so the ratio never exceeds 1).  cr, ci are compile-time
+// constants at every call site, so the branch and the division fold away.
+template <bool FWD>
+LITHO_HD void bfly_w(cplx e, cplx o, float cr, float ci, cplx& p, cplx& m) {
+    const float si = FWD ? -ci : ci;
+    const float acr = cr < 0.f ? -cr : cr, asi = si < 0.f ? -si : si;
+    float dx, dy, sc;
+    // explicit fmaf: keeps the compiler from sharing sc*d between the two outputs (mul + 2 adds = 8 ops)
+    if (acr >= asi) {
+        const float t = si / cr;
+        dx = fmaf(-t, o.y, o.x);
+        dy = fmaf(t, o.x, o.y);
+        sc = cr;
+    } else {
+        const float t = cr / si;
+        dx = fmaf(t, o.x, -o.y);
+        dy = fmaf(t, o.y, o.x);
+        sc = si;
+    }
+    p = mk(fmaf(sc, dx, e.x), fmaf(sc, dy, e.y));
+    m = mk(fmaf(-sc, dx, e.x), fmaf(-sc, dy, e.y));
+}
+
 template <bool FWD>
 LITHO_HD void dft2(cplx& a0, cplx& a1) {
     cplx t = a0;
@@ -43,14 +69,12 @@ LITHO_HD void dft8(cplx (&a)[8]) {
     dft4<FWD>(a[0], a[2], a[4], a[6]);  // E[k] in a[0],a[2],a[4],a[6]
     dft4<FWD>(a[1], a[3], a[5], a[7]);  // O[k] in a[1],a[3],a[5],a[7]
     cplx e0 = a[0], e1 = a[2], e2 = a[4], e3 = a[6];
-    cplx t0 = a[1];
-    cplx t1 = mul_w<FWD>(a[3], C, C);
+    cplx o0 = a[1], o1 = a[3], o3 = a[7];
     cplx t2 = mul_i<FWD>(a[5]);
-    cplx t3 = mul_w<FWD>(a[7], -C, C);
-    a[0] = cadd(e0, t0); a[4] = csub(e0, t0);
-    a[1] = cadd(e1, t1); a[5] = csub(e1, t1);
+    a[0] = cadd(e0, o0); a[4] = csub(e0, o0);
+    bfly_w<FWD>(e1, o1, C, C, a[1], a[5]);
     a[2] = cadd(e2, t2); a[6] = csub(e2, t2);
-    a[3] = cadd(e3, t3); a[7] = csub(e3, t3);
+    bfly_w<FWD>(e3, o3, -C, C, a[3], a[7]);
 }
 
 template <bool FWD>
@@ -66,20 +90,17 @@ LITHO_HD void dft16(cplx (&a)[16]) {
     }
     dft8<FWD>(e);
     dft8<FWD>(o);
-    cplx t[8];
-    t[0] = o[0];
-    t[1] = mul_w<FWD>(o[1], C1, S1);
-    t[2] = mul_w<FWD>(o[2], C2, C2);
-    t[3] = mul_w<FWD>(o[3], S1, C1);
-    t[4] = mul_i<FWD>(o[4]);
-    t[5] = mul_w<FWD>(o[5], -S1, C1);
-    t[6] = mul_w<FWD>(o[6], -C2, C2);
-    t[7] = mul_w<FWD>(o[7], -C1, S1);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        a[k] = cadd(e[k], t[k]);
-        a[k + 8] = csub(e[k], t[k]);
+    a[0] = cadd(e[0], o[0]); a[8] = csub(e[0], o[0]);
+    bfly_w<FWD>(e[1], o[1], C1, S1, a[1], a[9]);
+    bfly_w<FWD>(e[2], o[2], C2, C2, a[2], a[10]);
+    bfly_w<FWD>(e[3], o[3], S1, C1, a[3], a[11]);
+    {
+        const cplx t4 = mul_i<FWD>(o[4]);
+        a[4] = cadd(e[4], t4); a[12] = csub(e[4], t4);
     }
+    bfly_w<FWD>(e[5], o[5], -S1, C1, a[5], a[13]);
+    bfly_w<FWD>(e[6], o[6], -C2, C2, a[6], a[14]);
+    bfly_w<FWD>(e[7], o[7], -C1, S1, a[7], a[15]);
 }
 
 template <bool FWD>
@@ -105,12 +126,16 @@ LITHO_HD void dft32(cplx (&a)[32]) {
     dft16<FWD>(o);
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-        cplx t;
-        if (k == 0) t = o[0];
-        else if (k == 8) t = mul_i<FWD>(o[8]);
-        else t = mul_w<FWD>(o[k], C[k], S[k]);
-        a[k] = cadd(e[k], t);
-        a[k + 16] = csub(e[k], t);
+        if (k == 0) {
+            a[0] = cadd(e[0], o[0]);
+            a[16] = csub(e[0], o[0]);
+        } else if (k == 8) {
+            const cplx t = mul_i<FWD>(o[8]);
+            a[8] = cadd(e[8], t);
+            a[24] = csub(e[8], t);
+        } else {
+            bfly_w<FWD>(e[k], o[k], C[k], S[k], a[k], a[k + 16]);
+        }
     }
 }
 
