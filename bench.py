@@ -388,13 +388,23 @@ def run_ours(args):
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         step_ach = algorithmic_flops(pn, N, n_src)["total"] / (ms_per_step * 1e-3) / 1e12
+        # DRAM bytes per launch of the dominant kernel from the committed ncu capture (scaled by batch)
+        traffic, traffic_src = None, None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            if tj.get("config") == cfg.name and plan.path == 2:
+                traffic = (tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]) * batch / tj["batch"]
+                traffic_src = tj["source"]
+        except Exception:
+            pass
         roofline = {
             "bound": "fp32", "kernel": ("abbe_fast_cols_kernel" if plan.path == 2 else "abbe_cols_kernel") +
                       " (column pass + |E|^2 accumulate)",
             "achieved": achieved, "peak": best, "unit": "TFLOP/s", "frac": achieved / best if best else None,
             "peak_source": "FP32 FMA probe measured in this run (MEASURED_PEAKS.json has no FP32 entry); "
                            f"nominal {peak_nominal:.1f} TFLOP/s = SMs*128*2*max clock",
-            "flops_per_launch": cols_flops, "ms_per_launch": cols_ms, "traffic": None,
+            "flops_per_launch": cols_flops, "ms_per_launch": cols_ms, "traffic": traffic,
+            "traffic_source": traffic_src,
             "rows_kernel": {"achieved": (fl_alg["rows"] / kern["rows"]["launches"]) /
                             (kern["rows"]["ms_total"] / kern["rows"]["launches"] * 1e-3) / 1e12,
                             "ms_per_launch": kern["rows"]["ms_total"] / kern["rows"]["launches"]},

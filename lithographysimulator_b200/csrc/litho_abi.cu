@@ -617,9 +617,9 @@ int litho_plan_create_ex(int pn, int N, const int* bbox, int flags, litho_plan_t
     }
     // batch (source points per launch pair).  Generic path: T of one batch around 64 MB.  Fast path:
     // measured on B200 at cfg3 (profiles/): launches of 3 source points (T in L2) lose more to launch
-    // gaps, table loads and partial waves than batches of 12 lose to T spilling to HBM (47 vs 54.5
-    // images/s), so aim at ~200 MB per slot, at least 1, at most 16.
-    const size_t target = (p->path == 2) ? ((size_t)208 << 20) : ((size_t)64 << 20);
+    // gaps, table loads and partial waves than batches of 16 lose to T spilling to HBM (53.7 vs 64.5
+    // images/s), so aim at ~270 MB per slot, at least 1, at most 16.
+    const size_t target = (p->path == 2) ? ((size_t)272 << 20) : ((size_t)64 << 20);
     int b = (int)(target / (per ? per : 1));
     p->default_batch = b < 1 ? 1 : (b > 16 ? 16 : b);
     *out = p;
