@@ -53,9 +53,20 @@ struct FastShape {
 #ifndef LITHO_COL_THREADS
 #define LITHO_COL_THREADS 512
 #endif
-    static constexpr int CB = (LITHO_COL_THREADS / TG) >= 16 ? 16 : ((LITHO_COL_THREADS / TG) >= 4 ? (LITHO_COL_THREADS / TG) : 4);
-    static constexpr int COL_THREADS = CB * TG;
-    static constexpr size_t COL_SMEM = (size_t)(NTAB_PAD + CB * Sh::SMEM_ELEMS) * sizeof(cplx);
+    // COL_DUAL (M <= 1024): one CTA computes BOTH output-row residues of its tile -- threads [0,HALF) take
+    // rr = 0, [HALF,2*HALF) rr = 1 -- so the two halves request the same T sectors at the same time and
+    // the second request is served by L1 (T crosses L2/HBM once instead of twice).
+#ifndef LITHO_COL_DUAL
+#define LITHO_COL_DUAL 1
+#endif
+    static constexpr bool COL_DUAL = (LITHO_COL_DUAL != 0) && PPT == 32 && TG <= 32;
+    static constexpr int CB_SINGLE = (LITHO_COL_THREADS / TG) >= 16 ? 16 : ((LITHO_COL_THREADS / TG) >= 4 ? (LITHO_COL_THREADS / TG) : 4);
+    static constexpr int CB_DUAL = (256 / TG) >= 16 ? 16 : (256 / TG);
+    static constexpr int CB = COL_DUAL ? CB_DUAL : CB_SINGLE;
+    static constexpr int COL_HALF = CB * TG;                       // threads per residue
+    static constexpr int COL_THREADS = COL_DUAL ? 2 * COL_HALF : COL_HALF;
+    static constexpr int COL_GRID_Y = COL_DUAL ? 1 : 2;
+    static constexpr size_t COL_SMEM = (size_t)(NTAB_PAD + (COL_DUAL ? 2 : 1) * CB * Sh::SMEM_ELEMS) * sizeof(cplx);
     // occupancy targets: 4 registers per FFT point held -> 128 regs (PPT 32) / 64 regs (PPT 16) per thread
     static constexpr int TARGET_THREADS = PPT == 32 ? 512 : 1024;
     static constexpr int COL_MIN_BLOCKS = (TARGET_THREADS / COL_THREADS) >= 1 ? (TARGET_THREADS / COL_THREADS) : 1;
@@ -274,10 +285,12 @@ LITHO_HD void fast_cols_body(const FastColsParams& P, const Ctx& ctx, cplx* smem
     constexpr int CB = F::CB;
     cplx* tab = smem;
     fast_tables_begin<M, PPT>(P.tables, tab, ctx);  // lands while the first inputs are in flight
-    const int col = ctx.tid() % CB;
-    const int g = ctx.tid() / CB;
-    cplx* ex = smem + F::NTAB_PAD + col;
-    const int rr = ctx.by();
+    const int half = F::COL_DUAL ? ctx.tid() / F::COL_HALF : 0;
+    const int th = ctx.tid() - half * F::COL_HALF;
+    const int col = th % CB;
+    const int g = th / CB;
+    cplx* ex = smem + F::NTAB_PAD + (size_t)half * (CB * F::Sh::SMEM_ELEMS) + col;
+    const int rr = F::COL_DUAL ? half : ctx.by();
     constexpr int NBLK = M / CB;
     const int rc = ctx.bx() / NBLK;
     const int kc = (ctx.bx() - rc * NBLK) * CB + col;

@@ -135,13 +135,13 @@ int launch_fast_cols_m(const FastColsParams& P, litho_stream_t st) {
     const int gx = 2 * (M / F::CB);
 #if defined(LITHO_EMU)
     (void)st;
-    litho_emu::launch(gx, 2, 1, F::COL_THREADS, F::COL_SMEM,
+    litho_emu::launch(gx, F::COL_GRID_Y, 1, F::COL_THREADS, F::COL_SMEM,
                       [&](const litho_emu::EmuCtx& c, char* s) { fast_cols_body<M, PPT>(P, c, (cplx*)s); });
     return 0;
 #else
     int e = set_smem(abbe_fast_cols_kernel<M, PPT>, F::COL_SMEM);
     if (e) return e;
-    abbe_fast_cols_kernel<M, PPT><<<dim3(gx, 2, 1), dim3(F::COL_THREADS, 1, 1), F::COL_SMEM, st>>>(P);
+    abbe_fast_cols_kernel<M, PPT><<<dim3(gx, F::COL_GRID_Y, 1), dim3(F::COL_THREADS, 1, 1), F::COL_SMEM, st>>>(P);
     return (int)cudaGetLastError();
 #endif
 }
