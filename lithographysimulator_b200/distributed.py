@@ -12,7 +12,7 @@ import torch.distributed as dist
 
 from .imaging import AbbeEngine, _as_c64, _require_cuda, epsilon_n, source_shifts
 
-__all__ = ["shard_shifts", "abbe_image_sharded"]
+__all__ = ["shard_shifts", "abbe_image_sharded", "focus_sweep_sharded"]
 
 
 def shard_shifts(shifts: torch.Tensor, rank: int, world: int) -> torch.Tensor:
@@ -49,3 +49,45 @@ def abbe_image_sharded(mask, maskFT, pupilF, lightsource, pixelSize, deltaK, wav
         if world > 1:
             dist.all_reduce(intensity, op=dist.ReduceOp.SUM, group=group)
         return eng.finalize(plan, intensity, eps) if postprocess else eng.unpermute(plan, intensity)
+
+
+def focus_sweep_sharded(mask, maskFT, pupils, lightsource, pixelSize, deltaK, wavelength, device, *, group=None,
+                        batch: int = 0):
+    """Focus-exposure sweep (BASELINE cfg5): one aerial image per pupil function in `pupils`, the pupils
+    (focus values) sharded across the ranks -- independent images, so no reduce; every rank returns the
+    full list (images of other ranks are received with one all_gather per image slot).
+
+    With a single process it is simply a loop over the pupils that reuses the uploaded mask spectrum and
+    source-point list."""
+    dev = _require_cuda(device)
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    eng = AbbeEngine.get(dev)
+    with torch.cuda.device(dev):
+        maskFT_d = _as_c64(maskFT, dev)
+        pn = int(maskFT_d.shape[0])
+        eps, N = epsilon_n(deltaK, pixelSize, wavelength)
+        shifts_d = source_shifts(lightsource.to(dev), pn)
+        mine = {}
+        for i in range(rank, len(pupils), world):
+            pupil_d = _as_c64(pupils[i], dev)
+            plan = eng.plan_for(pn, N, eng.pupil_support(pupil_d), shifts_d)
+            intensity = eng.intensity_plane(plan)
+            eng.accumulate(plan, maskFT_d, pupil_d, shifts_d, intensity, None, batch)
+            mine[i] = eng.finalize(plan, intensity, eps)
+        if world == 1:
+            return [mine[i] for i in range(len(pupils))]
+        side = eng.plan(pn, N, (0, pn - 1, 0, pn - 1), generic=True).output_side(eps)
+        out = []
+        rounds = (len(pupils) + world - 1) // world
+        for rnd in range(rounds):
+            i = rnd * world + rank
+            local = mine.get(i)
+            if local is None:
+                local = torch.zeros((side, side), dtype=torch.float32, device=dev)
+            bufs = [torch.empty_like(local) for _ in range(world)]
+            dist.all_gather(bufs, local, group=group)
+            for r in range(world):
+                if rnd * world + r < len(pupils):
+                    out.append(bufs[r])
+        return out

@@ -256,6 +256,22 @@ def test_direct_solver_256_against_oracle(L, dev):
     assert O.rel_l2(img, ref) < H.TOL
 
 
+def test_focus_sweep_matches_single_images(L, dev):
+    """BASELINE cfg5 semantics at a small grid: one image per defocus value, same mask spectrum and source."""
+    from lithographysimulator_b200.distributed import focus_sweep_sharded
+    c = KAT["demo64_quasar"]
+    m = _mask_stub(L, 64, 25, dev)
+    pupils = []
+    for d in (-150.0, 0.0, 150.0):
+        ab = torch.tensor([0, 0, 0.01, 0, d, 0.01], dtype=torch.float16, device=dev)
+        pupils.append(L.Pupil(64, 193.0, 0.7, ab, dev).generatePupilFunction())
+    imgs = focus_sweep_sharded(m, _t(c["maskFT"], dev), pupils, _t(c["lightsource"], dev), 25, m.deltaK, 193.0, dev)
+    assert len(imgs) == 3
+    for img, pf in zip(imgs, pupils):
+        ref = O.abbe_image(c["maskFT"], pf.cpu().numpy(), c["lightsource"], 25, 4 / 64, 193.0, True, np.complex128)
+        assert O.rel_l2(img.cpu().numpy(), ref) < H.TOL
+
+
 def test_end_to_end_object_api(L, dev):
     """The reference demo (imageformation.py:99-119) through the object API, against its golden image."""
     c = KAT["demo64_quasar"]
