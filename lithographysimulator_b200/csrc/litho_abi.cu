@@ -769,6 +769,11 @@ int litho_abbe_fft_accumulate_ex(const litho_plan_t* p, const void* maskFT, cons
     if (batch > n_src) batch = n_src;
     if (!workspace || workspace_bytes < litho_plan_workspace_bytes(p, batch))
         return fail(LITHO_ERR_WORKSPACE, "accumulate: workspace too small for the requested batch");
+    // equal-sized batches (130 points with batch 16 -> 9 x 14..15 instead of 8 x 16 + a 2-point launch pair)
+    {
+        const int nbatches = (n_src + batch - 1) / batch;
+        batch = (n_src + nbatches - 1) / nbatches;
+    }
     litho_stream_t st = (litho_stream_t)stream;
     if (p->path == 2) {
         // fast coarse-grid kernels; the caller guarantees shifts inside plan.shift_range (no wrap)
