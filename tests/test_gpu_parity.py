@@ -376,3 +376,24 @@ def test_cfg5_size_fast_equals_generic(L, dev):
     num = torch.linalg.vector_norm((fast - gen).double())
     den = torch.linalg.vector_norm(gen.double())
     assert float(num / den) < H.TOL
+
+
+def test_cfg5_reference_pupil_against_oracle(L, dev):
+    """BASELINE cfg5 grid with the reference's own 8192-px pupil (support 4099 px, generic fine-grid kernels,
+    N = 16384): one source point against the oracle's FFT solver (complex64 here: a 16384^2 complex128 plane
+    would need 4 GB per copy; the oracle's c64/c128 gap is 1e-7)."""
+    from lithographysimulator_b200.imaging import AbbeEngine
+    pn = 8192
+    pf_ref, _ = O.pupil_function([0, 0, 0.01, 0, -150, 0.01], pn, 0.7, 193.0)
+    ab = torch.tensor([0, 0, 0.01, 0, -150, 0.01], dtype=torch.float16, device=dev)
+    pf = L.Pupil(pn, 193.0, 0.7, ab, dev).generatePupilFunction()
+    assert np.abs(pf.cpu().numpy() - pf_ref).max() < 2e-7
+    rng = np.random.default_rng(8)
+    mft = (rng.standard_normal((pn, pn), dtype=np.float32) + 1j * rng.standard_normal((pn, pn), dtype=np.float32))
+    mft = mft.astype(np.complex64)
+    sh = torch.tensor([[1500, -900]], dtype=torch.int32)
+    eng = AbbeEngine.get(dev)
+    img = eng.abbe_fft(_t(mft, dev), pf, None, 25, 4 / pn, 193.0, shifts=sh, postprocess=False).cpu().numpy()
+    e = O.calculate_fft_aerial(np.roll(pf_ref, (1500, -900), (0, 1)), mft, pn, 2 * pn, np.complex64)
+    ref = e.real.astype(np.float64) ** 2 + e.imag.astype(np.float64) ** 2
+    assert O.rel_l2(img, ref) < H.TOL
