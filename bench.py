@@ -39,8 +39,27 @@ UNIT = "images/s"
 
 
 # ----------------------------------------------------------------------------- workload
+def build_inputs_device(cfg_name: str, dev):
+    """Synthetic inputs of a BASELINE config built by the product's own builders on the GPU (native
+    kernels behind Mask.fraunhofer / LightSource / Pupil) -- the oracle is not involved in this arm."""
+    import torch
+    import lithographysimulator_b200 as L
+    from lithographysimulator_b200 import workloads as wl
+    cfg = wl.CONFIGS[cfg_name]
+    mask = L.Mask(torch.from_numpy(cfg.geometry()), cfg.pixel_size, dev)
+    mft = mask.fraunhofer(cfg.wavelength, True)
+    src = L.LightSource(cfg.sigma_in, cfg.sigma_out, cfg.pn, cfg.na, 0, 0, dev)
+    ls = src.generateQuasar(4, -math.pi / 8) if cfg.source == "quasar" else src.generateAnnular()
+    ls = ls * torch.from_numpy(wl.lattice(cfg.pn, cfg.stride)).to(dev)
+    ab = torch.tensor(cfg.aberrations, dtype=torch.float16, device=dev)
+    pf = L.Pupil(cfg.pn, cfg.wavelength, cfg.na, ab, dev).generatePupilFunction()
+    torch.cuda.synchronize(dev)
+    return cfg, mft, pf, ls
+
+
 def build_inputs_host(cfg_name: str):
-    """Synthetic inputs of a BASELINE config, built on the host with the oracle builders (numpy)."""
+    """Synthetic inputs of a BASELINE config, built on the host with the oracle builders (numpy); used by
+    the reference arm and the cpu_baseline leg only."""
     from oracle import abbe_oracle as O
     from lithographysimulator_b200 import workloads as wl
     cfg = wl.CONFIGS[cfg_name]
@@ -188,12 +207,10 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = _native.device_lib()
 
-    cfg, mft_h, pf_h, ls_h = build_inputs_host(args.config)
+    cfg, mft_d, pf_d, ls_d = build_inputs_device(args.config, dev)
     pn = cfg.pn
     eps, N = epsilon_n(4 / pn, cfg.pixel_size, cfg.wavelength)
-    mft_d = torch.from_numpy(mft_h).to(dev)
-    pf_d = torch.from_numpy(pf_h).to(dev)
-    ls_d = torch.from_numpy(ls_h).to(dev)
+    mft_h, pf_h, ls_h = mft_d.cpu().numpy(), pf_d.cpu().numpy(), ls_d.cpu().numpy()
     eng = AbbeEngine.get(dev)
     shifts_all = source_shifts(ls_d, pn)
     n_src = int(shifts_all.shape[0])
@@ -418,7 +435,8 @@ def run_ours(args):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            v, ns, _, dt = time_cpu_baseline(cfg, mft_h, pf_h, ls_h, max(threads, min(args.ref_sample, 4 * threads)),
+            _, o_mft, o_pf, o_ls = build_inputs_host(args.config)   # the baseline leg builds its own inputs
+            v, ns, _, dt = time_cpu_baseline(cfg, o_mft, o_pf, o_ls, max(threads, min(args.ref_sample, 4 * threads)),
                                              threads)
             cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": f"{ns} of {n_src} source points ({dt:.1f} s), extrapolated linearly in n_src; "
