@@ -232,7 +232,9 @@ def run_ours(args):
     reduce_work = [None, None]
     state = {"i": 0, "img": None}
 
-    def one_image():
+    def one_image(prep=None, out_host=None):
+        """One aerial image.  prep = None: inputs resident in HBM (`value`); otherwise a PreparedImage staged from
+        pinned host tensors by eng.prepare() on the copy stream (`e2e`), and the root copies the image to out_host."""
         i = state["i"]
         state["i"] += 1
         inten = planes[i % 2]
@@ -242,10 +244,18 @@ def run_ours(args):
         if fin_done[i % 2] is not None:
             main.wait_event(fin_done[i % 2])       # image i-2 has left this plane
         inten.zero_()
-        eng.accumulate(plan, mft_d, pf_d, shifts_mine, inten, None, args.batch)
+        if prep is None:
+            eng.accumulate(plan, mft_d, pf_d, shifts_mine, inten, None, args.batch)
+        else:
+            main.wait_event(prep.ready)
+            prep.shifts.record_stream(main)
+            eng.accumulate(prep.plan, prep.maskFT, prep.pupil, prep.shifts, inten, None, args.batch)
+            eng.consumed(prep)                      # the staging set may be refilled once this has run
         if args.no_pipeline:
             reduce_fn(inten)
             state["img"] = eng.finalize(plan, inten, eps)
+            if out_host is not None:
+                out_host.copy_(state["img"], non_blocking=True)
             return
         # one NCCL sum-reduce of the partial planes to a root that rotates with the image index, so the
         # post-processing of consecutive images is spread over the ranks instead of repeated on all of them
@@ -265,6 +275,8 @@ def run_ours(args):
             if work is not None:
                 work.wait()                         # fin_stream waits for the NCCL reduce
             state["img"] = eng.finalize(plan, inten, eps)
+            if out_host is not None:
+                out_host.copy_(state["img"], non_blocking=True)   # D2H of the result, off the compute stream
             done = torch.cuda.Event()
             done.record(fin_stream)
             fin_done[i % 2] = done
@@ -361,28 +373,36 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- end to end through the public API with host (pinned) tensors ----
+    # Every step: H2D of that image's mask spectrum, pupil and source (full [pn,pn] tensors, as the reference's
+    # abbeImage takes them) from pinned memory, source-point extraction, compute, D2H of the finished image.
+    # eng.prepare() stages image i+1 on the copy stream while image i is computed (two staging sets), and the
+    # D2H runs on the post-processing stream, so the copies overlap the kernels but are all inside the timed region.
     mft_p = torch.from_numpy(mft_h).pin_memory()
     pf_p = torch.from_numpy(pf_h).pin_memory()
-    ls_mine_h = np.zeros_like(ls_h)
-    idx = np.argwhere(ls_h != 0)[rank::world]
-    ls_mine_h[idx[:, 0], idx[:, 1]] = 1
-    ls_p = torch.from_numpy(ls_mine_h).pin_memory()
+    ls_p = torch.from_numpy(ls_h).pin_memory()
     side = plan.output_side(eps)
-    out_p = torch.empty((side, side), dtype=torch.float32).pin_memory()
-    mask_obj = None
+    out_p = [torch.empty((side, side), dtype=torch.float32).pin_memory() for _ in range(2)]
+    shard = (rank, world) if world > 1 else None
 
-    def e2e_once():
-        img_d = eng.abbe_fft(mft_p, pf_p, ls_p, cfg.pixel_size, 4 / pn, cfg.wavelength, reduce_fn=reduce_fn, plan=plan,
-                             batch=args.batch)
-        out_p.copy_(img_d, non_blocking=True)
+    def prepare(i):
+        return eng.prepare(mft_p, pf_p, ls_p, cfg.pixel_size, 4 / pn, cfg.wavelength, slot=i % 2, shard=shard,
+                           plan=plan)
+
+    def e2e_loop(n):
+        prep = prepare(0)
+        for i in range(n):
+            one_image(prep, out_p[i % 2])
+            prep = prepare(i + 1) if i + 1 < n else None    # staged while image i is being computed
+        join()
         torch.cuda.synchronize(dev)
 
-    e2e_once()
+    state["i"] = 0
+    e2e_loop(2)
     barrier()
+    e2e_steps = max(2, min(args.steps, 8))
+    state["i"] = 0
     t0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, 5))
-    for _ in range(e2e_steps):
-        e2e_once()
+    e2e_loop(e2e_steps)
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -390,7 +410,14 @@ def run_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te.item())
     h2d = mft_p.numel() * 8 + pf_p.numel() * 8 + ls_p.numel() * 8
-    d2h = out_p.numel() * 4
+    d2h = out_p[0].numel() * 4
+    # the image that came back over PCIe must be the image the resident-input path produced
+    e2e_check = None
+    if rank == (e2e_steps - 1) % world and state["img"] is not None:
+        ref_img = eng.abbe_fft(mft_d, pf_d, ls_d, cfg.pixel_size, 4 / pn, cfg.wavelength, plan=plan) if world == 1 else None
+        got = out_p[(e2e_steps - 1) % 2]
+        if ref_img is not None:
+            e2e_check = float((got.to(dev) - ref_img).norm() / ref_img.norm())
 
     if rank == 0:
         fl_alg = algorithmic_flops(pn, N, n_mine)
@@ -455,7 +482,11 @@ def run_ours(args):
                            if plan.path == 2 else "generic fine-grid", "sharding": f"source points interleaved over {world} rank(s), "
                                                                            "one NCCL all-reduce of the intensity plane"},
                 "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
-                "e2e": {"value": 1.0 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "e2e": {"value": 1.0 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "steps": e2e_steps, "rel_l2_vs_resident_path": e2e_check,
+                        "how": "pinned host tensors -> AbbeEngine.prepare() (H2D + source-point extraction on a copy "
+                               "stream, one image ahead) -> accumulate -> reduce -> finalize -> D2H on the "
+                               "post-processing stream; wall clock over the loop, max over ranks"},
                 "roofline": roofline, "cpu_baseline": cpu, "breakdown_ms": breakdown,
                 "wall_s_timed_region": t_wall}
         print(json.dumps(line), flush=True)

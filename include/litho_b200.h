@@ -79,6 +79,11 @@ int litho_plan_create_ex(int pn, int N, const int* support, int flags, litho_pla
 void litho_plan_destroy(litho_plan_t* plan);
 int litho_plan_get_info(const litho_plan_t* plan, litho_plan_info_t* info);
 size_t litho_plan_workspace_bytes(const litho_plan_t* plan, int batch);
+/* Columns per tile of the TMA-staged column-pass kernel this plan launches (the T tile of the next source
+ * point is copied global -> shared by cp.async.bulk.tensor while the current FFT runs); 0 when the plan
+ * uses the plain-load column kernel (generic path, sub-FFT > 1024, LITHO_TMA=0, or a driver without
+ * cuTensorMapEncodeTiled). */
+int litho_plan_column_tile(const litho_plan_t* plan);
 
 /* The hot loop of abbeImage                                  imageformation.py:59-67
  *   intensity += sum_s w_s * | centred zoom IDFT_N { roll(pupil, shift_s) * maskFT } |^2

@@ -43,6 +43,7 @@ SYMBOLS = [
     ("litho_plan_destroy", None, [_P]),
     ("litho_plan_get_info", C.c_int, [_P, C.POINTER(PlanInfo)]),
     ("litho_plan_workspace_bytes", C.c_size_t, [_P, C.c_int]),
+    ("litho_plan_column_tile", C.c_int, [_P]),
     ("litho_abbe_fft_accumulate", C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P, C.c_size_t, _P]),
     ("litho_abbe_fft_accumulate_ex", C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P, C.c_size_t, _P, C.c_int]),
     ("litho_mask_spectrum_workspace_bytes", C.c_size_t, [C.c_int, C.c_double, C.c_int]),
@@ -142,6 +143,10 @@ class Plan:
         self.lib.check(self.lib.litho_abbe_fft_accumulate_ex(self.handle, maskFT, pupil, shifts, weights, n_src, batch,
                                                              intensity, workspace, workspace_bytes, stream, phases),
                        "litho_abbe_fft_accumulate")
+
+    def column_tile(self) -> int:
+        """Columns per TMA-staged tile of the column pass (0: plain-load column kernel)."""
+        return int(self.lib.litho_plan_column_tile(self.handle))
 
     def output_side(self, eps: float) -> int:
         return int(self.lib.litho_fft_output_side(self.pn, eps))

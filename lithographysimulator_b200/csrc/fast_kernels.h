@@ -67,6 +67,17 @@ struct FastShape {
     static constexpr int COL_THREADS = COL_DUAL ? 2 * COL_HALF : COL_HALF;
     static constexpr int COL_GRID_Y = COL_DUAL ? 1 : 2;
     static constexpr size_t COL_SMEM = (size_t)(NTAB_PAD + (COL_DUAL ? 2 : 1) * CB * Sh::SMEM_ELEMS) * sizeof(cplx);
+    // TMA-staged variant of the column pass (COL_DUAL shapes, i.e. M <= 1024): the whole input tile of a source
+    // point (Sr rows x CB columns) is copied by the TMA engine into shared memory while the previous source
+    // point's FFT runs.  The tile is fetched in <= 5 boxes of <= 256 rows, each box a multiple of 128 bytes
+    // (TMA destination alignment: an even number of 64-byte rows), so the last box may overshoot Sr by
+    // < COL_TILE_SLACK rows.
+    static constexpr int COL_TILE_SLACK = 10;
+    static constexpr int COL_TILE_ROWS = M + 1 + COL_TILE_SLACK;
+    static constexpr size_t COL_TILE_OFF = (COL_SMEM + 127) / 128 * 128;
+    static constexpr size_t COL_BAR_OFF = COL_TILE_OFF + (size_t)COL_TILE_ROWS * CB * sizeof(cplx);
+    static constexpr size_t COL_SMEM_TMA = COL_BAR_OFF + 32;  // mbarrier + TileCtl
+    static constexpr bool COL_TMA = COL_DUAL && COL_SMEM_TMA <= 227 * 1024;
     // occupancy targets: 4 registers per FFT point held -> 128 regs (PPT 32) / 64 regs (PPT 16) per thread
     static constexpr int TARGET_THREADS = PPT == 32 ? 512 : 1024;
     static constexpr int COL_MIN_BLOCKS = (TARGET_THREADS / COL_THREADS) >= 1 ? (TARGET_THREADS / COL_THREADS) : 1;
@@ -114,6 +125,11 @@ struct FastColsParams {
     int s_begin;
     const cplx* tables;
     float* ic;  // [2][2][M][M] : ((rr*2 + rc)*M + kr)*M + kc, accumulated
+    // TMA-staged variant: T seen as one 2-D tensor (rows of M complex elements) starting at tile.base;
+    // row_begin = row of T[sl = 0][rc = 0][u = 0] of this launch in that tensor; nbox boxes per tile
+    int use_tma, nbox;
+    long long row_begin;
+    TileMap tile;
 };
 
 template <int M, int PPT, class Ctx>
@@ -321,6 +337,120 @@ LITHO_HD void fast_cols_body(const FastColsParams& P, const Ctx& ctx, cplx* smem
         for (int e = 0; e < PPT; ++e) acc[e] += w * cnorm2(v[e]);
     }
     if (P.batch == 0) fast_tables_wait(ctx);
+#pragma unroll
+    for (int e = 0; e < PPT; ++e) dst[(size_t)(TG * e) * M] = acc[e];
+}
+
+// TMA-staged column pass (FastShape::COL_TMA shapes).  Same arithmetic and thread mapping as fast_cols_body,
+// but the T tile of source point sl+1 is copied global -> shared by the TMA engine (one elected thread issues
+// nbox cp.async.bulk.tensor boxes that complete on an mbarrier) while the FFT of source point sl runs, and
+// both output-row residues read the staged tile from shared memory: the load latency leaves the critical
+// path and the LSU issues one 256-byte-contiguous LDS per warp instead of 64-byte global segments.
+// The tile buffer is single: every thread moves its inputs to registers first, and the CTA barrier that
+// precedes the first exchange of the FFT is also the point from which the buffer may be overwritten.
+// Loop state of the tile copies lives in shared memory (only thread 0 touches it), so that it costs no
+// registers in the FFT, whose 128-register budget is full.
+struct TileCtl {
+    int next_row;       // first tensor row of the next tile to fetch
+    int rows_per_tile;  // tensor rows between consecutive source points (2*Sr)
+    int remaining;      // tiles still to be fetched
+    int col;            // first column of this CTA's tile
+};
+
+template <class Ctx>
+struct TileHook {
+    const Ctx& ctx;
+    unsigned char* smem_raw;
+    const FastColsParams* P;
+    size_t tile_off, bar_off;
+    LITHO_HD void after_last_gather() const {}
+    LITHO_HD void after_first_sync() const {
+        if (ctx.tid() == 0) {
+            TileCtl* ctl = reinterpret_cast<TileCtl*>(smem_raw + bar_off + 16);
+            const int rem = ctl->remaining;
+            if (rem > 0) {
+                const int row = ctl->next_row;
+                ctx.tile_load(smem_raw + tile_off, P->tile, row, ctl->col, P->nbox,
+                              reinterpret_cast<unsigned long long*>(smem_raw + bar_off));
+                ctl->next_row = row + ctl->rows_per_tile;
+                ctl->remaining = rem - 1;
+            }
+        }
+    }
+};
+
+template <int M, int PPT, class Ctx>
+LITHO_HD void fast_cols_tma_body(const FastColsParams& P, const Ctx& ctx, unsigned char* smem_raw) {
+    using F = FastShape<M, PPT>;
+    constexpr int TG = F::TG;
+    constexpr int CB = F::CB;
+    static_assert(F::COL_DUAL, "TMA-staged column pass needs the dual-residue CTA shape");
+    cplx* smem = reinterpret_cast<cplx*>(smem_raw);
+    cplx* tab = smem;
+    const cplx* tile = reinterpret_cast<const cplx*>(smem_raw + F::COL_TILE_OFF);
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + F::COL_BAR_OFF);
+    fast_tables_begin<M, PPT>(P.tables, tab, ctx);
+    constexpr int NBLK = M / CB;
+    const int rc = ctx.bx() / NBLK;
+    if (ctx.tid() == 0) {
+        ctx.mbar_init(bar, 1);
+        TileCtl* ctl = reinterpret_cast<TileCtl*>(smem_raw + F::COL_BAR_OFF + 16);
+        ctl->next_row = (int)P.row_begin + rc * P.Sr;
+        ctl->rows_per_tile = 2 * P.Sr;
+        ctl->remaining = P.batch;
+        ctl->col = (ctx.bx() - rc * NBLK) * CB;
+    }
+    const int half = ctx.tid() / F::COL_HALF;
+    const int th = ctx.tid() - half * F::COL_HALF;
+    const int col = th % CB;
+    const int g = th / CB;
+    cplx* ex = smem + F::NTAB_PAD + (size_t)half * (CB * F::Sh::SMEM_ELEMS) + col;
+    const int rr = half;
+    const SmemTw<M, PPT> tw{tab};
+    const GroupSync<Ctx, 2> gs{ctx, 0, 0};
+    const TileHook<Ctx> hook{ctx, smem_raw, &P, F::COL_TILE_OFF, F::COL_BAR_OFF};
+
+    float* dst = P.ic + ((size_t)(rr * 2 + rc) * M + g) * M + (ctx.bx() - rc * NBLK) * CB + col;
+    float acc[PPT];
+#pragma unroll
+    for (int e = 0; e < PPT; ++e) acc[e] = dst[(size_t)(TG * e) * M];
+
+    fast_tables_wait(ctx);      // tables landed, barrier + loop state initialised (CTA barrier inside)
+    hook.after_first_sync();    // fetch the first tile
+    const int last = P.Sr - 1;
+
+    for (int sl = 0; sl < P.batch; ++sl) {
+        ctx.mbar_wait(bar, (unsigned)(sl & 1));
+        cplx v[PPT];
+        if (last >= M - 1) {
+#pragma unroll
+            for (int e = 0; e < PPT; ++e) v[e] = tile[th + e * (TG * CB)];
+        } else {
+#pragma unroll
+            for (int e = 0; e < PPT; ++e) {  // rows past Sr hold stale (finite or not) data: select, never multiply
+                const cplx x = tile[th + e * (TG * CB)];
+                const bool in = g + TG * e <= last;
+                v[e] = mk(in ? x.x : 0.f, in ? x.y : 0.f);
+            }
+        }
+        if (rr) {
+#pragma unroll
+            for (int e = 0; e < PPT; ++e) v[e] = cmul(v[e], tab[F::PRE_OFF + g + TG * e]);
+        }
+        if (P.Sr > M) {  // rim input u = M folds onto slot 0 with w_2M^(rr*M) = (-1)^rr
+            const cplx y = tile[M * CB + col];
+            const float sgn = (g == 0) ? (rr ? -1.f : 1.f) : 0.f;
+            v[0] = mk(v[0].x + sgn * y.x, v[0].y + sgn * y.y);
+        }
+        if constexpr (F::Sh::NP == 1) {  // single-pass FFT: no exchange, hence no barrier inside fft_run
+            ctx.sync();
+            hook.after_first_sync();
+        }
+        fft_run<M, PPT, false>(v, ex, CB, g, tw, gs, hook);
+        const float w = P.weights ? P.weights[P.s_begin + sl] : 1.f;
+#pragma unroll
+        for (int e = 0; e < PPT; ++e) acc[e] += w * cnorm2(v[e]);
+    }
 #pragma unroll
     for (int e = 0; e < PPT; ++e) dst[(size_t)(TG * e) * M] = acc[e];
 }

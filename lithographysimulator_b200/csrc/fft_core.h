@@ -59,8 +59,12 @@ LITHO_HD void dft_all(cplx (&v)[PPT]) {
 // Hook: hook.after_last_gather() runs once per FFT right after the last read of the exchange buffer
 // (before the last butterflies), i.e. at the point from which the buffer is free again -- the fast
 // column kernel uses it to start the asynchronous copy of its next input tile into that buffer.
+// hook.after_first_sync() runs once per multi-pass FFT right after the CTA/group barrier that precedes the first
+// scatter, i.e. when every thread of the group has consumed its inputs -- the TMA-staged column kernel uses it
+// to start the copy of the next input tile.
 struct NoHook {
     LITHO_HD void after_last_gather() const {}
+    LITHO_HD void after_first_sync() const {}
 };
 
 template <int M, int PPT, int PASS, bool FWD, class Tw, class Sync, class Hook>
@@ -98,6 +102,7 @@ LITHO_HD void fft_pass(cplx (&v)[PPT], cplx* sm, int es, int g, const Tw& tw, co
     if constexpr (!LAST) {
         // scatter: output t of butterfly j goes to (j-k)*R + k + t*NS
         sync.sync();
+        if constexpr (PASS == 0) hook.after_first_sync();
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
             const int j = g + b * TG;

@@ -116,6 +116,18 @@ LITHO_HD int cdiv(int a, int b) { return a >= 0 ? (a + b - 1) / b : -((-a) / b);
 // floor(a / b) for b > 0 and any sign of a
 LITHO_HD int fdiv(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
 
+// Column tile of the T ring as the TMA engine sees it: a 2-D tensor of float32 with 2*M floats per row
+// (one complex64 row of T) and `rows` rows.  `map` is the CUtensorMap of the device build (opaque here, 64-byte
+// aligned as the hardware requires); base/pitch/rows are the same facts in plain form, used by the CPU
+// emulation of the copy (tests/emu) and for bounds.
+struct alignas(64) TileMap {
+    unsigned char map[128];
+    const cplx* base;      // element (row 0, column 0)
+    long long pitch;       // elements per row
+    long long rows;        // rows of the tensor; boxes reaching past it are zero-filled
+    int box_rows, box_cols;  // box of one copy: box_rows x box_cols complex elements
+};
+
 #if defined(__CUDACC__)
 // Device thread context: thin wrapper over the CUDA built-ins.
 struct DevCtx {
@@ -138,6 +150,49 @@ struct DevCtx {
     // named barrier over `n` threads (a multiple of 32); id 0 is __syncthreads' barrier, use 1..15
     __device__ __forceinline__ void sync_named(int id, int n) const {
         asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+    }
+    // ---- TMA (cp.async.bulk.tensor) tile copies completing on a shared-memory mbarrier ----
+    // One thread initialises the barrier (followed by a CTA barrier before anybody waits on it).
+    __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) const {
+        const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // Issued by ONE thread: announce `bytes` on the barrier, then copy `nbox` boxes of the tile whose first
+    // element is (row, col) into consecutive box-sized pieces of `smem_dst` (128-byte aligned).
+    __device__ __forceinline__ void tile_load(void* smem_dst, const TileMap& tm, int row, int col, int nbox,
+                                              unsigned long long* bar) const {
+        const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+        const unsigned box_bytes = (unsigned)(tm.box_rows * tm.box_cols) * 8u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(box_bytes * (unsigned)nbox)
+                     : "memory");
+        unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+        const unsigned long long mp = reinterpret_cast<unsigned long long>(tm.map);
+#pragma unroll 1
+        for (int i = 0; i < nbox; ++i) {
+            const int x = 2 * col;                       // float32 coordinates
+            const int y = row + i * tm.box_rows;
+            asm volatile(
+                "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                ::"r"(d), "l"(mp), "r"(x), "r"(y), "r"(b)
+                : "memory");
+            d += box_bytes;
+        }
+    }
+    // All threads: wait until the copy announced for this phase has landed.  Bounded: a logic error gives
+    // wrong numbers (caught by the parity tests), never a hung GPU.
+    __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) const {
+        const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+        unsigned ok = 0;
+        for (int spins = 0; !ok && spins < (1 << 26); ++spins) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(ok)
+                : "r"(a), "r"(phase)
+                : "memory");
+        }
     }
 };
 #endif

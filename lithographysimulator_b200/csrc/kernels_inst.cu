@@ -111,6 +111,12 @@ abbe_fast_cols_kernel(const __grid_constant__ FastColsParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     fast_cols_body<M, PPT>(P, DevCtx{}, reinterpret_cast<cplx*>(smem_raw));
 }
+template <int M, int PPT>
+__global__ void __launch_bounds__(FastShape<M, PPT>::COL_THREADS, FastShape<M, PPT>::COL_MIN_BLOCKS)
+abbe_fast_cols_tma_kernel(const __grid_constant__ FastColsParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw_tma[];
+    if constexpr (FastShape<M, PPT>::COL_TMA) fast_cols_tma_body<M, PPT>(P, DevCtx{}, smem_raw_tma);
+}
 #endif
 
 template <int M, int PPT>
@@ -133,12 +139,27 @@ template <int M, int PPT>
 int launch_fast_cols_m(const FastColsParams& P, litho_stream_t st) {
     using F = FastShape<M, PPT>;
     const int gx = 2 * (M / F::CB);
+    if (P.use_tma && !F::COL_TMA) return -2;
 #if defined(LITHO_EMU)
     (void)st;
+    if constexpr (F::COL_TMA) {
+        if (P.use_tma) {
+            litho_emu::launch(gx, 1, 1, F::COL_THREADS, F::COL_SMEM_TMA, [&](const litho_emu::EmuCtx& c, char* s) {
+                fast_cols_tma_body<M, PPT>(P, c, (unsigned char*)s);
+            });
+            return 0;
+        }
+    }
     litho_emu::launch(gx, F::COL_GRID_Y, 1, F::COL_THREADS, F::COL_SMEM,
                       [&](const litho_emu::EmuCtx& c, char* s) { fast_cols_body<M, PPT>(P, c, (cplx*)s); });
     return 0;
 #else
+    if (P.use_tma) {
+        int e = set_smem(abbe_fast_cols_tma_kernel<M, PPT>, F::COL_SMEM_TMA);
+        if (e) return e;
+        abbe_fast_cols_tma_kernel<M, PPT><<<dim3(gx, 1, 1), dim3(F::COL_THREADS, 1, 1), F::COL_SMEM_TMA, st>>>(P);
+        return (int)cudaGetLastError();
+    }
     int e = set_smem(abbe_fast_cols_kernel<M, PPT>, F::COL_SMEM);
     if (e) return e;
     abbe_fast_cols_kernel<M, PPT><<<dim3(gx, F::COL_GRID_Y, 1), dim3(F::COL_THREADS, 1, 1), F::COL_SMEM, st>>>(P);
@@ -149,6 +170,11 @@ int launch_fast_cols_m(const FastColsParams& P, litho_stream_t st) {
 template <int M, int PPT>
 int fast_ntab_m() {
     return FastShape<M, PPT>::NTAB;
+}
+// columns per TMA-staged tile (0: shape has no TMA-staged column kernel)
+template <int M, int PPT>
+int fast_tma_cols_m() {
+    return FastShape<M, PPT>::COL_TMA ? FastShape<M, PPT>::CB : 0;
 }
 
 #if LITHO_INST_M >= 512 && LITHO_INST_M <= 2048
@@ -188,10 +214,12 @@ template int launch_fast_fused_m<LITHO_INST_M>(const FusedParams&, int, litho_st
 template int launch_fast_rows_m<LITHO_INST_M, 32>(const FastRowsParams&, int, litho_stream_t);
 template int launch_fast_cols_m<LITHO_INST_M, 32>(const FastColsParams&, litho_stream_t);
 template int fast_ntab_m<LITHO_INST_M, 32>();
+template int fast_tma_cols_m<LITHO_INST_M, 32>();
 #if defined(LITHO_WITH_PPT16)  // 16 points per thread: measured 2x slower on B200 (profiles/README.md), not built by default
 template int launch_fast_rows_m<LITHO_INST_M, 16>(const FastRowsParams&, int, litho_stream_t);
 template int launch_fast_cols_m<LITHO_INST_M, 16>(const FastColsParams&, litho_stream_t);
 template int fast_ntab_m<LITHO_INST_M, 16>();
+template int fast_tma_cols_m<LITHO_INST_M, 16>();
 #endif
 #endif
 

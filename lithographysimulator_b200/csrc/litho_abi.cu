@@ -268,6 +268,55 @@ static int get_twiddles(int L, cplx** out) {
     return 0;
 }
 
+// --------------------------------------------------------------------------- TMA tile map of the T ring
+// T (any number of [Sr][M] complex64 planes back to back) as a 2-D float32 tensor: 2*M floats per row.
+// The CUtensorMap is encoded through the driver entry point obtained from the runtime (no libcuda link).
+#if !defined(LITHO_EMU)
+#include <cuda.h>
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static encode_tiled_fn get_encode_tiled() {
+    static encode_tiled_fn fn = []() -> encode_tiled_fn {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return (encode_tiled_fn)ptr;
+    }();
+    return fn;
+}
+#endif
+
+// returns 0 on success; on failure the caller falls back to the plain-load column kernel
+static int make_tile_map(TileMap* tm, const void* base, int M, long long rows, int box_rows, int box_cols) {
+    memset(tm, 0, sizeof(*tm));
+    tm->base = (const cplx*)base; tm->pitch = M; tm->rows = rows;
+    tm->box_rows = box_rows; tm->box_cols = box_cols;
+#if !defined(LITHO_EMU)
+    static_assert(sizeof(CUtensorMap) == sizeof(tm->map), "CUtensorMap is 128 bytes");
+    encode_tiled_fn enc = get_encode_tiled();
+    if (!enc) return 1;
+    if (((uintptr_t)base & 15) != 0 || rows <= 0 || rows > 0x7fffffffLL) return 1;
+    const cuuint64_t gdim[2] = {(cuuint64_t)2 * M, (cuuint64_t)rows};
+    const cuuint64_t gstr[1] = {(cuuint64_t)M * sizeof(cplx)};
+    const cuuint32_t box[2] = {(cuuint32_t)2 * box_cols, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUtensorMapL2promotion l2 = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    if (const char* env = getenv("LITHO_TMA_L2")) {
+        const int v = atoi(env);
+        l2 = v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+           : v == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    }
+    const CUresult r = enc((CUtensorMap*)tm->map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr,
+                           box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, l2,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return 1;
+#endif
+    return 0;
+}
+
 // --------------------------------------------------------------------------- plan
 // T ring slots of the fast path: rows(b) may run LITHO_TSLOTS-1 batches ahead of cols(b)
 #define LITHO_TSLOTS 3
@@ -287,6 +336,7 @@ struct litho_plan {
     int ext[8];      // non-zero extents of the first/last window row and column (window coordinates)
     cplx* tables;    // device twiddle tables of the fast kernels (owned by the plan)
     int n_sm;
+    int tma_cols;    // > 0: columns per tile of the TMA-staged column kernel (0: plain global loads)
     int fused;       // 1: one persistent launch per accumulate call (fast_fused_body)
     int fused_B;     // source points per group of the fused kernel
     int* counters;   // device: work-queue index, dependency counters, error flag (owned by the plan)
@@ -330,6 +380,18 @@ static int dispatch_fast_fused(int M, const FusedParams& P, int gx, litho_stream
 #undef X
     }
     return -1;
+}
+static int dispatch_fast_tma_cols(int M, int ppt) {
+    switch (M) {
+#if defined(LITHO_WITH_PPT16)
+#define X(m) case m: return ppt == 16 ? fast_tma_cols_m<m, 16>() : fast_tma_cols_m<m, 32>();
+#else
+#define X(m) case m: return fast_tma_cols_m<m, 32>();
+#endif
+        LITHO_FOR_EACH_FAST_M(X)
+#undef X
+    }
+    return 0;
 }
 static int dispatch_fast_ntab(int M, int ppt) {
     switch (M) {
@@ -544,7 +606,7 @@ int litho_plan_create_ex(int pn, int N, const int* bbox, int flags, litho_plan_t
     size_t per = (size_t)p->zp.R * p->Sr * p->zp.Wr * sizeof(cplx);
     // ---- fast path eligibility: even window fit S <= Mf+1, coarse grid Nc = 2*Mf no finer than N ----
     p->path = 1; p->tables = nullptr; p->Mf = p->Nc = p->q = 0; p->rim_row = p->rim_col = 0;
-    p->fused = 0; p->fused_B = 2; p->counters = nullptr; p->counters_cap = 0;
+    p->fused = 0; p->fused_B = 2; p->counters = nullptr; p->counters_cap = 0; p->tma_cols = 0;
 #if !defined(LITHO_EMU)
     p->aux_stream = nullptr;
 #endif
@@ -617,6 +679,11 @@ int litho_plan_create_ex(int pn, int N, const int* bbox, int flags, litho_plan_t
             }
         }
         p->path = 2; p->Mf = Mf; p->Nc = 2 * Mf; p->q = N / (2 * Mf);
+        // TMA-staged column kernel where the shape has one (M <= 1024); LITHO_TMA=0 selects plain loads
+        p->tma_cols = dispatch_fast_tma_cols(Mf, p->ppt);
+        if (const char* env = getenv("LITHO_TMA")) {
+            if (atoi(env) == 0) p->tma_cols = 0;
+        }
         p->rim_row = (p->Sr == Mf + 1);
         p->rim_col = (p->Sc == Mf + 1);
         // extents in window coordinates, clamped to the window
@@ -683,6 +750,14 @@ int litho_plan_get_info(const litho_plan_t* p, litho_plan_info_t* info) {
     info->shift_range[0] = -p->bbox[0]; info->shift_range[1] = p->pn - 1 - p->bbox[1];
     info->shift_range[2] = -p->bbox[2]; info->shift_range[3] = p->pn - 1 - p->bbox[3];
     return LITHO_OK;
+}
+
+int litho_plan_column_tile(const litho_plan_t* p) {
+    if (!p || p->path != 2 || p->tma_cols <= 0) return 0;
+#if !defined(LITHO_EMU)
+    if (!get_encode_tiled()) return 0;
+#endif
+    return p->tma_cols;
 }
 
 static size_t align16(size_t b) { return (b + 15) / 16 * 16; }
@@ -832,6 +907,18 @@ int litho_abbe_fft_accumulate_ex(const litho_plan_t* p, const void* maskFT, cons
         const size_t slot_elems = (size_t)batch * 2 * p->Sr * p->Mf;
         cplx* Tslot[LITHO_TSLOTS];
         for (int i = 0; i < LITHO_TSLOTS; ++i) Tslot[i] = (cplx*)workspace + (size_t)i * slot_elems;
+        // one tensor map over the whole ring; a tile = Sr rows x tma_cols columns fetched in nbox boxes
+        if (p->tma_cols > 0 && (phases & 2)) {
+            // boxes of <= 256 rows whose byte size is a multiple of 128 (alignment of the TMA destination)
+            int nbox = (p->Sr + 255) / 256;
+            int box_rows = ((p->Sr + nbox - 1) / nbox + 1) & ~1;
+            if (box_rows > 256) { ++nbox; box_rows = ((p->Sr + nbox - 1) / nbox + 1) & ~1; }
+            if (nbox <= 5 && make_tile_map(&fc.tile, workspace, p->Mf, (long long)LITHO_TSLOTS * batch * 2 * p->Sr, box_rows,
+                              p->tma_cols) == 0) {
+                fc.use_tma = 1;
+                fc.nbox = nbox;
+            }
+        }
 #if !defined(LITHO_EMU)
         const bool overlap = (phases == 3) && p->aux_stream != nullptr;
         if (overlap) {
@@ -846,6 +933,7 @@ int litho_abbe_fft_accumulate_ex(const litho_plan_t* p, const void* maskFT, cons
             const int nb = (n_src - s0) < batch ? (n_src - s0) : batch;
             fr.s_begin = s0; fr.batch = nb; fr.T = Tslot[b % LITHO_TSLOTS];
             fc.s_begin = s0; fc.batch = nb; fc.T = Tslot[b % LITHO_TSLOTS];
+            fc.row_begin = (long long)(b % LITHO_TSLOTS) * batch * 2 * p->Sr;
 #if !defined(LITHO_EMU)
             if (overlap) {
                 if (b >= LITHO_TSLOTS) BE_CHECK((int)cudaStreamWaitEvent(p->aux_stream, p->ev_cols[b % LITHO_TSLOTS], 0));

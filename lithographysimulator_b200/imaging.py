@@ -18,7 +18,8 @@ import torch
 
 from . import _native
 
-__all__ = ["abbeImage", "calculateFFTAerial", "calculateAerial", "AbbeEngine", "source_shifts", "epsilon_n"]
+__all__ = ["abbeImage", "calculateFFTAerial", "calculateAerial", "AbbeEngine", "PreparedImage", "source_shifts",
+           "epsilon_n"]
 
 
 def _require_cuda(device) -> torch.device:
@@ -45,6 +46,16 @@ def _as_c64(t: torch.Tensor, dev: torch.device) -> torch.Tensor:
     return t.to(device=dev, dtype=torch.complex64, non_blocking=True).contiguous()
 
 
+class PreparedImage:
+    """Inputs of one aerial image staged on the device by AbbeEngine.prepare()."""
+
+    __slots__ = ("slot", "maskFT", "pupil", "shifts", "plan", "eps", "ready")
+
+    def __init__(self, slot, maskFT, pupil, shifts, plan, eps, ready):
+        self.slot, self.maskFT, self.pupil, self.shifts = slot, maskFT, pupil, shifts
+        self.plan, self.eps, self.ready = plan, eps, ready
+
+
 class AbbeEngine:
     """Per-device cache of plans and workspaces for the FFT-approximation path."""
 
@@ -56,6 +67,9 @@ class AbbeEngine:
         self.lib = _native.device_lib()
         self._plans: dict = {}
         self._workspaces: dict = {}
+        self._staging: dict = {}        # (slot, pn, source dtype) -> device copies of maskFT, pupil, lightsource
+        self._staging_busy: dict = {}   # slot -> event of the last run() that read the set
+        self._copy = None
 
     @classmethod
     def get(cls, device) -> "AbbeEngine":
@@ -160,6 +174,80 @@ class AbbeEngine:
             if reduce_fn is not None:
                 reduce_fn(intensity)
             return self.finalize(plan, intensity, eps) if postprocess else self.unpermute(plan, intensity)
+
+    # -- pipelined form of abbe_fft: stage inputs one image ahead --------------------------------
+    def prepare(self, maskFT, pupilF, lightsource, pixelSize, deltaK, wavelength, *, stream=None, slot: int = 0,
+                shard=None, generic: bool = False, plan: _native.Plan | None = None) -> "PreparedImage":
+        """First half of abbe_fft: upload the (host or device) inputs and extract the source points on `stream`
+        (default: a per-engine copy stream), without touching the compute stream.  Host tensors should be
+        pinned.  `slot` (0/1) selects one of two device staging sets, so that image i+1 can be prepared while
+        image i is being computed; a set is reused only after the run() that consumed it has finished (the
+        copy stream waits for that run's event).  `shard = (rank, world)` keeps every world-th source point."""
+        dev = self.device
+        st = stream if stream is not None else self._copy_stream()
+        with torch.cuda.device(dev), torch.cuda.stream(st):
+            prev = self._staging_busy.get(slot)
+            if prev is not None:
+                st.wait_event(prev)
+            pn = int(maskFT.shape[0])
+            bufs = self._staging.get((slot, pn, lightsource.dtype))
+            if bufs is None:
+                bufs = self._staging[(slot, pn, lightsource.dtype)] = (
+                    torch.empty((pn, pn), dtype=torch.complex64, device=dev),
+                    torch.empty((pn, pn), dtype=torch.complex64, device=dev),
+                    torch.empty((pn, pn), dtype=lightsource.dtype, device=dev))
+            mft_d, pf_d, ls_d = bufs
+            mft_d.copy_(maskFT, non_blocking=True)
+            pf_d.copy_(pupilF, non_blocking=True)
+            ls_d.copy_(lightsource, non_blocking=True)
+            eps, N = epsilon_n(deltaK, pixelSize, wavelength)
+            shifts_all = source_shifts(ls_d, pn)       # host sync on the copy stream only
+            if plan is None:
+                support = self.lib.pupil_support(pf_d.data_ptr(), pn, st.cuda_stream)
+                if generic:
+                    plan = self.plan(pn, N, support, generic=True)
+                else:
+                    plan = self.plan(pn, N, support)
+                    if plan.path == 2:
+                        n = int(shifts_all.shape[0])
+                        bounds = self.lib.shift_bounds(shifts_all.data_ptr() if n else None, n, st.cuda_stream)
+                        if not plan.shifts_fit(bounds):
+                            plan = self.plan(pn, N, support, generic=True)
+            shifts = shifts_all if shard is None else shifts_all[shard[0]::shard[1]].contiguous()
+            ready = torch.cuda.Event()
+            ready.record(st)
+        return PreparedImage(slot, mft_d, pf_d, shifts, plan, eps, ready)
+
+    def run(self, prep: "PreparedImage", *, batch: int = 0, reduce_fn=None, postprocess: bool = True,
+            finalize: bool = True):
+        """Second half of abbe_fft on the current stream: accumulate, optional `reduce_fn(intensity)`, post-process.
+        With finalize=False the (reduced) intensity plane is left to the caller (ranks that are not the root of a
+        rooted reduce) and None is returned."""
+        dev = self.device
+        with torch.cuda.device(dev):
+            cur = torch.cuda.current_stream(dev)
+            cur.wait_event(prep.ready)
+            prep.shifts.record_stream(cur)        # allocated on the copy stream, read by kernels of this one
+            intensity = self.intensity_plane(prep.plan)
+            self.accumulate(prep.plan, prep.maskFT, prep.pupil, prep.shifts, intensity, None, batch)
+            self.consumed(prep)                   # the staging set is free once the accumulation has read it
+            if reduce_fn is not None:
+                reduce_fn(intensity)
+            if not finalize:
+                return None
+            return self.finalize(prep.plan, intensity, prep.eps) if postprocess else self.unpermute(prep.plan, intensity)
+
+    def consumed(self, prep: "PreparedImage"):
+        """Mark `prep`'s staging set as read by everything enqueued so far on the current stream (for callers
+        that drive accumulate() themselves instead of run())."""
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream(self.device))
+        self._staging_busy[prep.slot] = done
+
+    def _copy_stream(self) -> torch.cuda.Stream:
+        if self._copy is None:
+            self._copy = torch.cuda.Stream(self.device)
+        return self._copy
 
     def fft_field(self, pf, maskFT, pixelNumber: int, N: int) -> torch.Tensor:
         dev = self.device

@@ -7,6 +7,8 @@
 #pragma once
 #include <ucontext.h>
 
+#include "hd.h"
+
 #include <cstdlib>
 #include <cstring>
 #include <functional>
@@ -62,6 +64,19 @@ struct EmuCtx {
     // asynchronous copies complete immediately in the emulation
     void cp_async16(void* dst, const void* src) const { memcpy(dst, src, 16); }
     void cp_async_wait() const {}
+    // TMA tile copies complete at issue in the emulation (boxes past the tensor's last row are zero-filled,
+    // like the hardware's out-of-bounds fill); the barrier is then always satisfied
+    void mbar_init(unsigned long long*, int) const {}
+    void tile_load(void* dst, const litho::TileMap& tm, int row, int col, int nbox, unsigned long long*) const {
+        char* d = (char*)dst;
+        for (int i = 0; i < nbox; ++i)
+            for (int r = 0; r < tm.box_rows; ++r, d += (size_t)tm.box_cols * 8) {
+                const long long y = row + (long long)i * tm.box_rows + r;
+                if (y < tm.rows) memcpy(d, tm.base + y * tm.pitch + col, (size_t)tm.box_cols * 8);
+                else memset(d, 0, (size_t)tm.box_cols * 8);
+            }
+    }
+    void mbar_wait(unsigned long long*, unsigned) const {}
 };
 
 // run one CTA of `nthreads` fibers; body(ctx) is the kernel body bound to its parameters

@@ -81,6 +81,7 @@ def emu_abbe_fft(maskFT, pupil, lightsource, pixel_size, wavelength, batch=0, we
     else:
         out = np.zeros((pn, pn), dtype=np.float32)
         plan.unpermute(_ptr(inten), _ptr(out), _ptr(fws), fwb)
-    info = dict(N=N, eps=eps, M=plan.M, R=plan.R, path=plan.path, support=support, n_src=n_src, bounds=bounds)
+    info = dict(N=N, eps=eps, M=plan.M, R=plan.R, path=plan.path, support=support, n_src=n_src, bounds=bounds,
+                column_tile=plan.column_tile())
     plan.close()
     return out, info

@@ -63,6 +63,29 @@ def test_emu_fast_path_dense_window(pn, ps, win):
     assert O.rel_l2(fast, gen) < H.TOL
 
 
+@pytest.mark.parametrize("tma", ["1", "0"])
+def test_emu_column_pass_tma_and_plain_agree(monkeypatch, tma):
+    """The TMA-staged column kernel (tile of source point sl+1 copied to shared memory while sl is transformed)
+    and the plain-load one share the arithmetic: both must match the oracle, with batches that make the tile
+    ring wrap (5 source points, batch 2 -> 3 launches over the 3 slots) and with a short window (Sr < M:
+    masked rows) as well as the full rim case (Sr = M+1)."""
+    monkeypatch.setenv("LITHO_TMA", tma)
+    for pn, win in ((128, 33), (128, 27)):
+        rng = np.random.default_rng(100 + win)
+        lo = pn // 2 - win // 2
+        pup = np.zeros((pn, pn), np.complex64)
+        pup[lo:lo + win, lo:lo + win] = rng.standard_normal((win, win)) + 1j * rng.standard_normal((win, win))
+        mft = (rng.standard_normal((pn, pn)) + 1j * rng.standard_normal((pn, pn))).astype(np.complex64)
+        shifts = np.array([[0, 0], [5, -7], [-3, 9], [3, 3], [-11, 2]], np.int32)
+        w = np.array([1.0, 2.0, 0.5, 1.5, 0.25], np.float32)
+        img, info = H.emu_abbe_fft(mft, pup, None, 25.0, 193.0, shifts=shifts, weights=w, postprocess=False, batch=2)
+        assert info["path"] == 2 and (info["column_tile"] > 0) == (tma == "1"), info
+        ref = np.zeros((pn, pn))
+        for (d0, d1), wi in zip(shifts, w):
+            ref += wi * np.abs(O.calculate_fft_aerial(np.roll(pup, (d0, d1), (0, 1)), mft, pn, 256)) ** 2
+        assert O.rel_l2(img, ref) < H.TOL
+
+
 def test_emu_fast_path_subfft_256():
     """pn = 512 -> sub-FFT 256 = radix 32 x 8 (two passes with a partial second radix)."""
     c_pn = 512

@@ -272,6 +272,70 @@ def test_focus_sweep_matches_single_images(L, dev):
         assert O.rel_l2(img.cpu().numpy(), ref) < H.TOL
 
 
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3"])
+def test_tma_staged_column_pass_equals_plain_loads(L, dev, name):
+    """Column pass with the T tile staged in shared memory by the TMA engine (cp.async.bulk.tensor + mbarrier,
+    the default for sub-FFT <= 1024) against the same pass with plain global loads (LITHO_TMA=0), and both
+    against the oracle on a few source points.  Uneven batches make the 3-slot T ring wrap."""
+    import os
+    from lithographysimulator_b200 import _native
+    cfg, mft, pf, ls = _cfg_inputs(name)
+    lib = _native.device_lib()
+    pn, N = cfg.pn, 2 * cfg.pn
+    sh = torch.from_numpy(O.source_shifts(ls, pn))[::13][:23].contiguous().to(dev)
+    w = torch.linspace(0.5, 2.0, sh.shape[0], device=dev)
+    mft_d, pf_d = _t(mft, dev), _t(pf, dev)
+    support = lib.pupil_support(pf_d.data_ptr(), pn, 0)
+    outs = {}
+    for tma in ("1", "0"):
+        os.environ["LITHO_TMA"] = tma
+        try:
+            plan = lib.plan_create(pn, N, support)     # the toggle is read when a plan is created
+        finally:
+            os.environ.pop("LITHO_TMA", None)
+        assert plan.path == 2 and (plan.column_tile() > 0) == (tma == "1")
+        inten = torch.zeros(plan.intensity_elems, dtype=torch.float32, device=dev)
+        wsb = plan.workspace_bytes(4)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        plan.accumulate(mft_d.data_ptr(), pf_d.data_ptr(), sh.data_ptr(), w.data_ptr(), sh.shape[0], 4,
+                        inten.data_ptr(), ws.data_ptr(), wsb, torch.cuda.current_stream(dev).cuda_stream)
+        out = torch.empty((pn, pn), dtype=torch.float32, device=dev)
+        fwb = plan.finalize_workspace_bytes()
+        fws = torch.empty(max(fwb, 16), dtype=torch.uint8, device=dev)
+        plan.unpermute(inten.data_ptr(), out.data_ptr(), fws.data_ptr(), fwb, torch.cuda.current_stream(dev).cuda_stream)
+        torch.cuda.synchronize(dev)
+        outs[tma] = out.cpu().numpy()
+        plan.close()
+    assert O.rel_l2(outs["1"], outs["0"]) < 1e-6
+    if pn <= 1024:   # the oracle takes seconds per source point beyond that; cfg3 is pinned by the golden sample test
+        ref = np.zeros((pn, pn))
+        for (d0, d1), wi in zip(sh.cpu().numpy(), w.cpu().numpy()):
+            ref += wi * np.abs(O.calculate_fft_aerial(np.roll(pf, (int(d0), int(d1)), (0, 1)), mft, pn, N)) ** 2
+        assert O.rel_l2(outs["1"], ref) < H.TOL
+
+
+def test_prepare_run_pipeline_matches_single_call(L, dev):
+    """AbbeEngine.prepare()/run() (inputs staged from pinned host memory on a copy stream, one image ahead)
+    returns the image abbeImage() returns, also when two images with different sources are in flight."""
+    from lithographysimulator_b200.imaging import AbbeEngine
+    cfg, mft, pf, ls = _cfg_inputs("cfg2")
+    eng = AbbeEngine.get(dev)
+    ls2 = ls * wl.lattice(cfg.pn, 3 * cfg.stride)
+    host = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (mft, pf, ls, ls2)]
+    args = (cfg.pixel_size, 4 / cfg.pn, cfg.wavelength)
+    p0 = eng.prepare(host[0], host[1], host[2], *args, slot=0)
+    p1 = eng.prepare(host[0], host[1], host[3], *args, slot=1)
+    i0 = eng.run(p0)
+    p2 = eng.prepare(host[0], host[1], host[3], *args, slot=0)   # refills set 0 behind run(p0)
+    i1 = eng.run(p1)
+    i2 = eng.run(p2)
+    torch.cuda.synchronize(dev)
+    m = _mask_stub(L, cfg.pn, cfg.pixel_size, dev)
+    r0 = L.abbeImage(m, host[0], host[1], host[2], *args, True, dev)
+    r1 = L.abbeImage(m, host[0], host[1], host[3], *args, True, dev)
+    assert torch.equal(i0, r0) and torch.equal(i1, r1) and torch.equal(i2, r1)
+
+
 def test_end_to_end_object_api(L, dev):
     """The reference demo (imageformation.py:99-119) through the object API, against its golden image."""
     c = KAT["demo64_quasar"]
