@@ -245,7 +245,7 @@ def run_ours(args):
             main.wait_event(fin_done[i % 2])       # image i-2 has left this plane
         inten.zero_()
         if prep is None:
-            eng.accumulate(plan, mft_d, pf_d, shifts_mine, inten, None, args.batch)
+            eng.accumulate(plan, mft_d, pf_d, shifts_mine, inten, None, args.batch, inputs_ready=not args.no_chain)
         else:
             main.wait_event(prep.ready)
             prep.shifts.record_stream(main)
@@ -505,6 +505,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--generic", action="store_true", help="force the generic fine-grid kernels")
+    ap.add_argument("--no-chain", action="store_true", help="row pass of image i+1 waits for image i's last column pass")
     ap.add_argument("--no-pipeline", action="store_true", help="finalize each image before starting the next")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -95,9 +95,14 @@ int litho_abbe_fft_accumulate(const litho_plan_t* plan, const void* maskFT, cons
                               const int32_t* shifts, const float* weights, int n_src, int batch,
                               float* intensity, void* workspace, size_t workspace_bytes, void* stream);
 
-/* Same as litho_abbe_fft_accumulate with a phase mask for profiling: bit 0 = row pass, bit 1 = column
- * pass (3 = both).  Running one pass alone re-uses whatever T holds, so results are only
- * meaningful with both bits set; bench.py uses the single-pass forms to time each kernel live. */
+/* Same as litho_abbe_fft_accumulate with a phase mask: bit 0 = row pass, bit 1 = column pass (3 = both).
+ * Running one pass alone re-uses whatever T holds, so results are only meaningful with both bits set;
+ * bench.py uses the single-pass forms to time each kernel live.
+ * LITHO_PHASE_INPUTS_READY (bit 2): maskFT, pupil and shifts are already valid on the device when the call is
+ * made (not produced by work still queued on `stream`).  The row pass of this call may then start while
+ * earlier work on `stream` (typically the last column pass of the previous image on the same plan and
+ * workspace) is still running; the column passes and the intensity plane stay ordered on `stream`. */
+#define LITHO_PHASE_INPUTS_READY 4
 int litho_abbe_fft_accumulate_ex(const litho_plan_t* plan, const void* maskFT, const void* pupil,
                                  const int32_t* shifts, const float* weights, int n_src, int batch,
                                  float* intensity, void* workspace, size_t workspace_bytes, void* stream,

@@ -25,6 +25,7 @@ class PlanInfo(C.Structure):
                 ("intensity_elems", C.c_uint64), ("shift_range", C.c_int * 4)]
 
 PLAN_GENERIC = 1
+PHASE_INPUTS_READY = 4  # litho_abbe_fft_accumulate_ex: inputs valid on the device at call time
 
 
 # every symbol include/litho_b200.h declares: (name, restype, argtypes)

@@ -337,6 +337,11 @@ struct litho_plan {
     cplx* tables;    // device twiddle tables of the fast kernels (owned by the plan)
     int n_sm;
     int tma_cols;    // > 0: columns per tile of the TMA-staged column kernel (0: plain global loads)
+    // T ring bookkeeping across accumulate calls (LITHO_PHASE_INPUTS_READY): which ring the ev_cols events of
+    // the last call refer to
+    mutable const void* last_ws;
+    mutable int last_batch;
+    mutable int cols_recorded[LITHO_TSLOTS];
     int fused;       // 1: one persistent launch per accumulate call (fast_fused_body)
     int fused_B;     // source points per group of the fused kernel
     int* counters;   // device: work-queue index, dependency counters, error flag (owned by the plan)
@@ -607,6 +612,8 @@ int litho_plan_create_ex(int pn, int N, const int* bbox, int flags, litho_plan_t
     // ---- fast path eligibility: even window fit S <= Mf+1, coarse grid Nc = 2*Mf no finer than N ----
     p->path = 1; p->tables = nullptr; p->Mf = p->Nc = p->q = 0; p->rim_row = p->rim_col = 0;
     p->fused = 0; p->fused_B = 2; p->counters = nullptr; p->counters_cap = 0; p->tma_cols = 0;
+    p->last_ws = nullptr; p->last_batch = 0;
+    for (int i = 0; i < LITHO_TSLOTS; ++i) p->cols_recorded[i] = 0;
 #if !defined(LITHO_EMU)
     p->aux_stream = nullptr;
 #endif
@@ -861,7 +868,7 @@ int litho_abbe_fft_accumulate_ex(const litho_plan_t* p, const void* maskFT, cons
         memset(&fc, 0, sizeof(fc));
         fc.T = (const cplx*)workspace; fc.Sr = p->Sr; fc.weights = weights; fc.tables = p->tables;
         fc.ic = intensity;
-        const bool use_fused = p->fused && phases == 3 &&
+        const bool use_fused = p->fused && (phases & 3) == 3 &&
                                workspace_bytes >= 2 * (size_t)p->fused_B * 2 * p->Sr * p->Mf * sizeof(cplx);
         if (use_fused) {
             // one persistent launch per chunk of <= 65536 groups (counter capacity)
@@ -920,11 +927,20 @@ int litho_abbe_fft_accumulate_ex(const litho_plan_t* p, const void* maskFT, cons
             }
         }
 #if !defined(LITHO_EMU)
-        const bool overlap = (phases == 3) && p->aux_stream != nullptr;
-        if (overlap) {
+        const bool overlap = ((phases & 3) == 3) && p->aux_stream != nullptr;
+        // LITHO_PHASE_INPUTS_READY: the row pass only reads the inputs and writes T, so it need not wait for
+        // what the caller's stream is still doing (the previous image's last column pass, the zeroing of the
+        // plane): its only dependencies are the column passes that last read each ring slot, which the plan's
+        // events already track when the ring is the one the previous call used.
+        const bool chained = overlap && (phases & LITHO_PHASE_INPUTS_READY) && p->last_ws == workspace &&
+                             p->last_batch == batch;
+        if (overlap && !chained) {
             BE_CHECK((int)cudaEventRecord(p->ev_start, st));
             BE_CHECK((int)cudaStreamWaitEvent(p->aux_stream, p->ev_start, 0));
+            for (int i = 0; i < LITHO_TSLOTS; ++i) p->cols_recorded[i] = 0;
         }
+        p->last_ws = overlap ? workspace : nullptr;   // single-pass (profiling) calls break the chain
+        p->last_batch = batch;
 #else
         const bool overlap = false;
 #endif
@@ -936,12 +952,14 @@ int litho_abbe_fft_accumulate_ex(const litho_plan_t* p, const void* maskFT, cons
             fc.row_begin = (long long)(b % LITHO_TSLOTS) * batch * 2 * p->Sr;
 #if !defined(LITHO_EMU)
             if (overlap) {
-                if (b >= LITHO_TSLOTS) BE_CHECK((int)cudaStreamWaitEvent(p->aux_stream, p->ev_cols[b % LITHO_TSLOTS], 0));
+                if (p->cols_recorded[b % LITHO_TSLOTS])
+                    BE_CHECK((int)cudaStreamWaitEvent(p->aux_stream, p->ev_cols[b % LITHO_TSLOTS], 0));
                 BE_CHECK(dispatch_fast_rows(p->Mf, p->ppt, fr, p->n_sm * (p->ppt == 16 ? 4 : 2), p->aux_stream));
                 BE_CHECK((int)cudaEventRecord(p->ev_rows[b % LITHO_TSLOTS], p->aux_stream));
                 BE_CHECK((int)cudaStreamWaitEvent(st, p->ev_rows[b % LITHO_TSLOTS], 0));
                 BE_CHECK(dispatch_fast_cols(p->Mf, p->ppt, fc, st));
                 BE_CHECK((int)cudaEventRecord(p->ev_cols[b % LITHO_TSLOTS], st));
+                p->cols_recorded[b % LITHO_TSLOTS] = 1;
                 continue;
             }
 #endif

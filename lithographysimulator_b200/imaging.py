@@ -115,8 +115,11 @@ class AbbeEngine:
         return ws
 
     # -- hot path --------------------------------------------------------------------------
-    def accumulate(self, plan: _native.Plan, maskFT_d, pupil_d, shifts_d, intensity, weights_d=None, batch: int = 0):
-        """intensity += sum_s w_s |IDFT{roll(P, shift_s) * M}|^2 (residue-major plane of `plan`)."""
+    def accumulate(self, plan: _native.Plan, maskFT_d, pupil_d, shifts_d, intensity, weights_d=None, batch: int = 0,
+                   inputs_ready: bool = False):
+        """intensity += sum_s w_s |IDFT{roll(P, shift_s) * M}|^2 (residue-major plane of `plan`).
+        inputs_ready: the input tensors are already valid on the device (not produced by work still queued on
+        the current stream), so the row pass may overlap the tail of the previous image (LITHO_PHASE_INPUTS_READY)."""
         n_src = int(shifts_d.shape[0])
         if n_src == 0:
             return
@@ -127,7 +130,8 @@ class AbbeEngine:
         ws = self.workspace(wsb)
         plan.accumulate(maskFT_d.data_ptr(), pupil_d.data_ptr(), shifts_d.data_ptr(),
                         None if weights_d is None else weights_d.data_ptr(), n_src, batch,
-                        intensity.data_ptr(), ws.data_ptr(), wsb, self.stream())
+                        intensity.data_ptr(), ws.data_ptr(), wsb, self.stream(),
+                        phases=3 | (_native.PHASE_INPUTS_READY if inputs_ready else 0))
 
     def intensity_plane(self, plan: _native.Plan) -> torch.Tensor:
         return torch.zeros(plan.intensity_elems, dtype=torch.float32, device=self.device)

@@ -9,6 +9,7 @@
 
 #include "hd.h"
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
@@ -22,11 +23,22 @@ struct Fiber {
     bool done = false;
 };
 
+// A barrier with real arrival counting: a thread that arrives waits (yielding) until all `n` participants of
+// this generation have arrived, so threads may yield any number of times elsewhere (mbarrier waits) without
+// slipping through a barrier, and mismatched barriers deadlock visibly instead of passing silently.
+struct Bar {
+    int arrived = 0;
+    unsigned gen = 0;
+};
+
 struct Sched {
     ucontext_t main_uc;
     std::vector<Fiber> fibers;
     int current = -1;
     std::function<void(int)> body;  // body(tid)
+    Bar cta_bar[16];                // id 0 = __syncthreads, 1..15 named barriers
+    std::vector<Bar> warp_bar;      // __syncwarp, one per warp
+    long progress = 0;              // bumped whenever a barrier or an mbarrier phase completes
 };
 
 inline Sched*& cur_sched() {
@@ -48,6 +60,18 @@ inline void fiber_yield() {
     swapcontext(&s->fibers[me].uc, &s->main_uc);
 }
 
+inline void barrier_wait(Bar& b, int n) {
+    Sched* s = cur_sched();
+    const unsigned g = b.gen;
+    if (++b.arrived >= n) {
+        b.arrived = 0;
+        ++b.gen;
+        ++s->progress;
+    } else {
+        while (b.gen == g) fiber_yield();
+    }
+}
+
 struct EmuCtx {
     int tid_, bdim_, bx_, by_, bz_, gdx_;
     int tid() const { return tid_; }
@@ -56,18 +80,21 @@ struct EmuCtx {
     int by() const { return by_; }
     int bz() const { return bz_; }
     int gdx() const { return gdx_; }
-    void sync() const { fiber_yield(); }
-    // a warp barrier is emulated by the (stronger) CTA-wide phase boundary; every thread of the CTA
-    // executes the same number of them in the kernels that use it
-    void sync_warp() const { fiber_yield(); }
-    void sync_named(int, int) const { fiber_yield(); }
+    void sync() const { barrier_wait(cur_sched()->cta_bar[0], bdim_); }
+    void sync_warp() const {
+        const int w = tid_ / 32;
+        const int n = (bdim_ - w * 32) < 32 ? (bdim_ - w * 32) : 32;
+        barrier_wait(cur_sched()->warp_bar[w], n);
+    }
+    void sync_named(int id, int n) const { barrier_wait(cur_sched()->cta_bar[id & 15], n); }
     // asynchronous copies complete immediately in the emulation
     void cp_async16(void* dst, const void* src) const { memcpy(dst, src, 16); }
     void cp_async_wait() const {}
     // TMA tile copies complete at issue in the emulation (boxes past the tensor's last row are zero-filled,
-    // like the hardware's out-of-bounds fill); the barrier is then always satisfied
-    void mbar_init(unsigned long long*, int) const {}
-    void tile_load(void* dst, const litho::TileMap& tm, int row, int col, int nbox, unsigned long long*) const {
+    // like the hardware's out-of-bounds fill).  The mbarrier word counts completed phases; a waiter yields
+    // until the phase of its parity has completed, as the hardware's try_wait.parity loop does.
+    void mbar_init(unsigned long long* bar, int) const { *bar = 0; }
+    void tile_load(void* dst, const litho::TileMap& tm, int row, int col, int nbox, unsigned long long* bar) const {
         char* d = (char*)dst;
         for (int i = 0; i < nbox; ++i)
             for (int r = 0; r < tm.box_rows; ++r, d += (size_t)tm.box_cols * 8) {
@@ -75,8 +102,12 @@ struct EmuCtx {
                 if (y < tm.rows) memcpy(d, tm.base + y * tm.pitch + col, (size_t)tm.box_cols * 8);
                 else memset(d, 0, (size_t)tm.box_cols * 8);
             }
+        ++*bar;
+        ++cur_sched()->progress;
     }
-    void mbar_wait(unsigned long long*, unsigned) const {}
+    void mbar_wait(unsigned long long* bar, unsigned parity) const {
+        while (!(*bar > 0 && ((*bar - 1) & 1) == parity)) fiber_yield();
+    }
 };
 
 // run one CTA of `nthreads` fibers; body(ctx) is the kernel body bound to its parameters
@@ -89,6 +120,7 @@ void run_cta(int nthreads, int bx, int by, int bz, int gdx, Body body) {
         EmuCtx ctx{tid, nthreads, bx, by, bz, gdx};
         body(ctx);
     };
+    s.warp_bar.resize((nthreads + 31) / 32);
     cur_sched() = &s;
     for (int t = 0; t < nthreads; ++t) {
         Fiber& f = s.fibers[t];
@@ -100,13 +132,23 @@ void run_cta(int nthreads, int bx, int by, int bz, int gdx, Body body) {
         makecontext(&f.uc, (void (*)())fiber_entry, 0);
     }
     bool any = true;
+    int idle_sweeps = 0;
     while (any) {
         any = false;
+        const long before = s.progress;
+        int finished = 0;
         for (int t = 0; t < nthreads; ++t) {
             if (s.fibers[t].done) continue;
             s.current = t;
             swapcontext(&s.main_uc, &s.fibers[t].uc);
             if (!s.fibers[t].done) any = true;
+            else ++finished;
+        }
+        // a sweep in which no barrier completed and no thread finished means the CTA is deadlocked
+        idle_sweeps = (s.progress == before && finished == 0) ? idle_sweeps + 1 : 0;
+        if (idle_sweeps > 4) {
+            fprintf(stderr, "litho_emu: CTA (%d,%d,%d) deadlocked (mismatched barrier or mbarrier never completed)\n", bx, by, bz);
+            abort();
         }
     }
     for (auto& f : s.fibers) free(f.stack);
