@@ -181,12 +181,17 @@ class AbbeEngine:
 
     # -- pipelined form of abbe_fft: stage inputs one image ahead --------------------------------
     def prepare(self, maskFT, pupilF, lightsource, pixelSize, deltaK, wavelength, *, stream=None, slot: int = 0,
-                shard=None, generic: bool = False, plan: _native.Plan | None = None) -> "PreparedImage":
+                shard=None, generic: bool = False, plan: _native.Plan | None = None,
+                upload_group=None) -> "PreparedImage":
         """First half of abbe_fft: upload the (host or device) inputs and extract the source points on `stream`
         (default: a per-engine copy stream), without touching the compute stream.  Host tensors should be
         pinned.  `slot` (0/1) selects one of two device staging sets, so that image i+1 can be prepared while
         image i is being computed; a set is reused only after the run() that consumed it has finished (the
-        copy stream waits for that run's event).  `shard = (rank, world)` keeps every world-th source point."""
+        copy stream waits for that run's event).  `shard = (rank, world)` keeps every world-th source point.
+        `upload_group` (a torch.distributed group, all ranks passing the same host inputs): every rank uploads only
+        its 1/world slice of each tensor over PCIe and the slices are exchanged with one all-gather per tensor over
+        NVLink, instead of every rank pulling the full tensors through the host's memory system at once.  Give it
+        a group of its own (dist.new_group) so that it does not queue behind the intensity reduce."""
         dev = self.device
         st = stream if stream is not None else self._copy_stream()
         with torch.cuda.device(dev), torch.cuda.stream(st):
@@ -201,9 +206,12 @@ class AbbeEngine:
                     torch.empty((pn, pn), dtype=torch.complex64, device=dev),
                     torch.empty((pn, pn), dtype=lightsource.dtype, device=dev))
             mft_d, pf_d, ls_d = bufs
-            mft_d.copy_(maskFT, non_blocking=True)
-            pf_d.copy_(pupilF, non_blocking=True)
-            ls_d.copy_(lightsource, non_blocking=True)
+            if upload_group is not None and shard is not None and shard[1] > 1:
+                self._sharded_upload(bufs, (maskFT, pupilF, lightsource), shard, upload_group, slot)
+            else:
+                mft_d.copy_(maskFT, non_blocking=True)
+                pf_d.copy_(pupilF, non_blocking=True)
+                ls_d.copy_(lightsource, non_blocking=True)
             eps, N = epsilon_n(deltaK, pixelSize, wavelength)
             shifts_all = source_shifts(ls_d, pn)       # host sync on the copy stream only
             if plan is None:
@@ -240,6 +248,28 @@ class AbbeEngine:
             if not finalize:
                 return None
             return self.finalize(prep.plan, intensity, prep.eps) if postprocess else self.unpermute(prep.plan, intensity)
+
+    def _sharded_upload(self, dev_bufs, host_tensors, shard, group, slot):
+        """H2D of this rank's byte slice of each input + all-gather of the slices (current stream = copy stream)."""
+        import torch.distributed as dist
+        rank, world = shard
+        for k, (full, src) in enumerate(zip(dev_bufs, host_tensors)):
+            src = src.contiguous()
+            if src.dtype != full.dtype:
+                src = src.to(full.dtype)
+            flat_dst = torch.view_as_real(full).view(-1).view(torch.uint8) if full.is_complex() else full.view(-1).view(torch.uint8)
+            flat_src = torch.view_as_real(src).view(-1).view(torch.uint8) if src.is_complex() else src.view(-1).view(torch.uint8)
+            n = flat_dst.numel()
+            if n % world or flat_src.device.type == "cuda":
+                full.copy_(src, non_blocking=True)      # ragged split or already on a device: plain copy
+                continue
+            chunk = n // world
+            key = ("part", slot, k, chunk)
+            part = self._staging.get(key)
+            if part is None:
+                part = self._staging[key] = torch.empty(chunk, dtype=torch.uint8, device=self.device)
+            part.copy_(flat_src[rank * chunk:(rank + 1) * chunk], non_blocking=True)
+            dist.all_gather_into_tensor(flat_dst, part, group=group)
 
     def consumed(self, prep: "PreparedImage"):
         """Mark `prep`'s staging set as read by everything enqueued so far on the current stream (for callers

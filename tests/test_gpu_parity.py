@@ -366,6 +366,16 @@ def _dist_worker(rank, world, port, out_path):
         m = L.Mask(torch.zeros((cfg.pn, cfg.pn), dtype=torch.int16), cfg.pixel_size, dev)
         img = abbe_image_sharded(m, torch.from_numpy(z["maskFT"]), torch.from_numpy(z["pupil"]), torch.from_numpy(ls),
                                  cfg.pixel_size, m.deltaK, cfg.wavelength, dev)
+        # pipelined form: each rank uploads half of every input tensor, the halves are all-gathered over NVLink
+        from lithographysimulator_b200.imaging import AbbeEngine
+        eng = AbbeEngine.get(dev)
+        up = dist.new_group(backend="nccl")
+        host = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (z["maskFT"], z["pupil"], ls)]
+        prep = eng.prepare(host[0], host[1], host[2], cfg.pixel_size, m.deltaK, cfg.wavelength, shard=(rank, world),
+                           upload_group=up)
+        img2 = eng.run(prep, reduce_fn=lambda t: dist.all_reduce(t))
+        torch.cuda.synchronize(dev)
+        assert torch.equal(img, img2), "sharded upload + prepare/run differs from abbe_image_sharded"
         if rank == 0:
             np.save(out_path, img.cpu().numpy())
     finally:
