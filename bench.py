@@ -341,8 +341,7 @@ def run_ours(args):
     # ---- per-kernel timing (live, CUDA events on the launching stream, after the timed region) ----
     inten = eng.intensity_plane(plan)
     n_mine = int(shifts_mine.shape[0])
-    batch = args.batch if args.batch > 0 else plan.default_batch
-    batch = max(1, min(batch, n_mine))
+    batch = eng.batch_for(plan, n_mine, args.batch)
     wsb = plan.workspace_bytes(batch)
     ws = eng.workspace(wsb)
     kern = {}

@@ -703,12 +703,13 @@ int litho_plan_create_ex(int pn, int N, const int* bbox, int flags, litho_plan_t
         per = (size_t)2 * p->Sr * Mf * sizeof(cplx);
     }
     // batch (source points per launch pair).  Generic path: T of one batch around 64 MB.  Fast path:
-    // measured on B200 at cfg3 (profiles/): launches of 3 source points (T in L2) lose more to launch
-    // gaps, table loads and partial waves than batches of 16 lose to T spilling to HBM (53.7 vs 64.5
-    // images/s), so aim at ~270 MB per slot, at least 1, at most 16.
-    const size_t target = (p->path == 2) ? ((size_t)272 << 20) : ((size_t)64 << 20);
+    // measured on B200 at cfg3 (profiles/README.md): per-launch costs (table loads, the read-modify-write of
+    // the intensity plane, partial waves, launch gaps) outweigh keeping T in L2 -- 58 / 67 / 73 / 76 / 77
+    // images/s at batches of 4 / 8 / 16 / 32 / 48 -- so aim at ~800 MB per ring slot, at most 48 points.
+    const size_t target = (p->path == 2) ? ((size_t)816 << 20) : ((size_t)64 << 20);
     int b = (int)(target / (per ? per : 1));
-    p->default_batch = b < 1 ? 1 : (b > 16 ? 16 : b);
+    const int cap = (p->path == 2) ? 48 : 16;
+    p->default_batch = b < 1 ? 1 : (b > cap ? cap : b);
     *out = p;
     return LITHO_OK;
 }
@@ -847,7 +848,13 @@ int litho_abbe_fft_accumulate_ex(const litho_plan_t* p, const void* maskFT, cons
     if (n_src < 0) return fail(LITHO_ERR_ARG, "accumulate: negative n_src");
     if (n_src == 0) return LITHO_OK;
     if (!shifts) return fail(LITHO_ERR_ARG, "accumulate: shifts is null");
-    if (batch <= 0) batch = p->default_batch;
+    if (batch <= 0) {
+        // default: the plan's batch, but at least 4 batches per call so that the row pass of one batch
+        // overlaps the column pass of the previous one (short source lists, e.g. one rank's shard)
+        batch = p->default_batch;
+        const int q = (n_src + 3) / 4;
+        if (q < batch) batch = q < 1 ? 1 : q;
+    }
     if (batch > n_src) batch = n_src;
     if (!workspace || workspace_bytes < litho_plan_workspace_bytes(p, batch))
         return fail(LITHO_ERR_WORKSPACE, "accumulate: workspace too small for the requested batch");

@@ -123,15 +123,21 @@ class AbbeEngine:
         n_src = int(shifts_d.shape[0])
         if n_src == 0:
             return
-        if batch <= 0:
-            batch = plan.default_batch
-        batch = min(batch, n_src)
+        batch = self.batch_for(plan, n_src, batch)
         wsb = plan.workspace_bytes(batch)
         ws = self.workspace(wsb)
         plan.accumulate(maskFT_d.data_ptr(), pupil_d.data_ptr(), shifts_d.data_ptr(),
                         None if weights_d is None else weights_d.data_ptr(), n_src, batch,
                         intensity.data_ptr(), ws.data_ptr(), wsb, self.stream(),
                         phases=3 | (_native.PHASE_INPUTS_READY if inputs_ready else 0))
+
+    @staticmethod
+    def batch_for(plan: _native.Plan, n_src: int, batch: int = 0) -> int:
+        """Source points per launch pair: the plan's default (sized from measurements), but at least 4 batches per
+        call so that row and column passes overlap -- the rule litho_abbe_fft_accumulate applies for batch <= 0."""
+        if batch <= 0:
+            batch = min(plan.default_batch, max(1, -(-n_src // 4)))
+        return max(1, min(batch, n_src))
 
     def intensity_plane(self, plan: _native.Plan) -> torch.Tensor:
         return torch.zeros(plan.intensity_elems, dtype=torch.float32, device=self.device)
