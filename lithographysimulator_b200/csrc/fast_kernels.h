@@ -67,17 +67,6 @@ struct FastShape {
     static constexpr int COL_THREADS = COL_DUAL ? 2 * COL_HALF : COL_HALF;
     static constexpr int COL_GRID_Y = COL_DUAL ? 1 : 2;
     static constexpr size_t COL_SMEM = (size_t)(NTAB_PAD + (COL_DUAL ? 2 : 1) * CB * Sh::SMEM_ELEMS) * sizeof(cplx);
-    // TMA-staged variant of the column pass (COL_DUAL shapes, i.e. M <= 1024): the whole input tile of a source
-    // point (Sr rows x CB columns) is copied by the TMA engine into shared memory while the previous source
-    // point's FFT runs.  The tile is fetched in <= 5 boxes of <= 256 rows, each box a multiple of 128 bytes
-    // (TMA destination alignment: an even number of 64-byte rows), so the last box may overshoot Sr by
-    // < COL_TILE_SLACK rows.
-    static constexpr int COL_TILE_SLACK = 10;
-    static constexpr int COL_TILE_ROWS = M + 1 + COL_TILE_SLACK;
-    static constexpr size_t COL_TILE_OFF = (COL_SMEM + 127) / 128 * 128;
-    static constexpr size_t COL_BAR_OFF = COL_TILE_OFF + (size_t)COL_TILE_ROWS * CB * sizeof(cplx);
-    static constexpr size_t COL_SMEM_TMA = COL_BAR_OFF + 32;  // mbarrier + TileCtl
-    static constexpr bool COL_TMA = COL_DUAL && COL_SMEM_TMA <= 227 * 1024;
     // occupancy targets: 4 registers per FFT point held -> 128 regs (PPT 32) / 64 regs (PPT 16) per thread
     static constexpr int TARGET_THREADS = PPT == 32 ? 512 : 1024;
     static constexpr int COL_MIN_BLOCKS = (TARGET_THREADS / COL_THREADS) >= 1 ? (TARGET_THREADS / COL_THREADS) : 1;
@@ -127,8 +116,10 @@ struct FastColsParams {
     float* ic;  // [2][2][M][M] : ((rr*2 + rc)*M + kr)*M + kc, accumulated
     // TMA-staged variant: T seen as one 2-D tensor (rows of M complex elements) starting at tile.base;
     // row_begin = row of T[sl = 0][rc = 0][u = 0] of this launch in that tensor; nbox boxes per tile
-    int use_tma, nbox;
+    // TMA-staged variant (fast_cols_tma_body): use_tma = columns per tile (0: plain loads)
+    int use_tma, nbox, rim;      // boxes per tile; rim: the tile has the extra row u = M (Sr == M+1)
     long long row_begin;
+    const cplx* tables_c;        // compact twiddle tables (TmaShape layout)
     TileMap tile;
 };
 
@@ -341,13 +332,61 @@ LITHO_HD void fast_cols_body(const FastColsParams& P, const Ctx& ctx, cplx* smem
     for (int e = 0; e < PPT; ++e) dst[(size_t)(TG * e) * M] = acc[e];
 }
 
-// TMA-staged column pass (FastShape::COL_TMA shapes).  Same arithmetic and thread mapping as fast_cols_body,
-// but the T tile of source point sl+1 is copied global -> shared by the TMA engine (one elected thread issues
-// nbox cp.async.bulk.tensor boxes that complete on an mbarrier) while the FFT of source point sl runs, and
-// both output-row residues read the staged tile from shared memory: the load latency leaves the critical
-// path and the LSU issues one 256-byte-contiguous LDS per warp instead of 64-byte global segments.
-// The tile buffer is single: every thread moves its inputs to registers first, and the CTA barrier that
-// precedes the first exchange of the FFT is also the point from which the buffer may be overwritten.
+// ----------------------------------------------------------------------------- TMA-staged column pass
+// Same arithmetic and thread mapping as fast_cols_body (dual-residue CTA: threads [0,HALF) compute output-row
+// residue rr = 0, [HALF,2*HALF) rr = 1 of the same CBT-column tile), but the T tile of source point sl+1 is copied
+// global -> shared by the TMA engine (one elected thread issues <= 4 cp.async.bulk.tensor boxes of M/4 rows plus
+// one 1-D bulk copy for the rim row u = M; all complete on one mbarrier) while the FFT of source point sl runs,
+// and both residues read the staged tile from shared memory: the load latency leaves the critical path and the
+// LSU issues one 256-byte-contiguous LDS per warp instead of 64-byte global segments.  The tile buffer is
+// single: every thread moves its inputs to registers first, and the CTA barrier that precedes the first exchange
+// of the FFT is also the point from which the buffer may be overwritten.
+//
+// CBT = columns per tile.  "Wide" tiles (CBT = FastShape::CB_DUAL: 8 at M = 1024) fill an SM with one 512-thread
+// CTA; "narrow" tiles (half of that) need half the shared memory, so two independent 256-thread CTAs share an SM
+// and the shared-memory bursts of one overlap the butterflies of the other.
+//
+// Shared-memory twiddle tables are compact here: pre[u] = w_2M^u only for u = 0..M/2 (the upper half follows
+// from w_2M^(M-u) = -conj(w_2M^u)), then tw1, tw2 as in FastShape.
+template <int M, int PPT, int CBT>
+struct TmaShape {
+    using F = FastShape<M, PPT>;
+    using Sh = typename F::Sh;
+    static constexpr int TG = F::TG;
+    static constexpr int HALF = CBT * TG;
+    static constexpr int THREADS = 2 * HALF;
+    static constexpr int PRE_N = M / 2 + 1;
+    static constexpr int TW1_OFF = (PRE_N + 1) & ~1;
+    static constexpr int TW2_OFF = TW1_OFF + (F::R1 - 1) * F::NS1;
+    static constexpr int NTAB = TW2_OFF + (F::R2 - 1) * F::NS2;
+    static constexpr int NTAB_PAD = (NTAB + 1) & ~1;
+    static constexpr int BOX_ROWS = M / 4 > 256 ? 256 : M / 4;     // rows per TMA box (<= 4 boxes cover u < M)
+    static constexpr size_t EX_BYTES = (size_t)2 * CBT * Sh::SMEM_ELEMS * sizeof(cplx);
+    static constexpr size_t TILE_OFF = ((size_t)NTAB_PAD * sizeof(cplx) + EX_BYTES + 127) / 128 * 128;
+    static constexpr size_t TILE_BYTES = ((size_t)(M + 1) * CBT * sizeof(cplx) + 15) / 16 * 16;
+    static constexpr size_t BAR_OFF = TILE_OFF + TILE_BYTES;
+    static constexpr size_t SMEM = BAR_OFF + 48;  // mbarrier (8, padded to 16) + TileCtl
+    // a box must be a multiple of 128 bytes (TMA destination alignment) and a half at least one warp... no: the
+    // halves only meet at CTA barriers, so any THREADS that is a multiple of 32 works
+    static constexpr bool OK = PPT == 32 && M >= 32 && M <= 2048 && CBT >= 2 && (M % CBT) == 0 &&
+                               ((size_t)BOX_ROWS * CBT * sizeof(cplx)) % 128 == 0 && THREADS % 32 == 0 &&
+                               THREADS <= 512 && SMEM <= 227 * 1024;
+    // two CTAs per SM when registers (128/thread) and shared memory (+1 KB reserved per CTA) allow
+    static constexpr int MIN_BLOCKS = (2 * THREADS * 128 <= 65536 && 2 * (SMEM + 1024) <= 228 * 1024) ? 2 : 1;
+};
+
+template <int M, int PPT, int CBT>
+struct TmaTw {
+    const cplx* tab;
+    template <int PASS>
+    LITHO_HD cplx get(int t, int k) const {
+        using S = TmaShape<M, PPT, CBT>;
+        using F = FastShape<M, PPT>;
+        if constexpr (PASS == 1) return tab[S::TW1_OFF + (t - 1) * F::NS1 + k];
+        else return tab[S::TW2_OFF + (t - 1) * F::NS2 + k];
+    }
+};
+
 // Loop state of the tile copies lives in shared memory (only thread 0 touches it), so that it costs no
 // registers in the FFT, whose 128-register budget is full.
 struct TileCtl {
@@ -363,6 +402,7 @@ struct TileHook {
     unsigned char* smem_raw;
     const FastColsParams* P;
     size_t tile_off, bar_off;
+    int rim_elem;   // element offset of the rim row inside the tile buffer (M * CBT)
     LITHO_HD void after_last_gather() const {}
     LITHO_HD void after_first_sync() const {
         if (ctx.tid() == 0) {
@@ -370,7 +410,7 @@ struct TileHook {
             const int rem = ctl->remaining;
             if (rem > 0) {
                 const int row = ctl->next_row;
-                ctx.tile_load(smem_raw + tile_off, P->tile, row, ctl->col, P->nbox,
+                ctx.tile_load(smem_raw + tile_off, P->tile, row, ctl->col, P->nbox, P->rim ? rim_elem : -1,
                               reinterpret_cast<unsigned long long*>(smem_raw + bar_off));
                 ctl->next_row = row + ctl->rows_per_tile;
                 ctl->remaining = rem - 1;
@@ -379,38 +419,39 @@ struct TileHook {
     }
 };
 
-template <int M, int PPT, class Ctx>
+// grid.x = 2*M/CBT column blocks (rc major), block = TmaShape::THREADS
+template <int M, int PPT, int CBT, class Ctx>
 LITHO_HD void fast_cols_tma_body(const FastColsParams& P, const Ctx& ctx, unsigned char* smem_raw) {
     using F = FastShape<M, PPT>;
+    using S = TmaShape<M, PPT, CBT>;
     constexpr int TG = F::TG;
-    constexpr int CB = F::CB;
-    static_assert(F::COL_DUAL, "TMA-staged column pass needs the dual-residue CTA shape");
     cplx* smem = reinterpret_cast<cplx*>(smem_raw);
     cplx* tab = smem;
-    const cplx* tile = reinterpret_cast<const cplx*>(smem_raw + F::COL_TILE_OFF);
-    unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + F::COL_BAR_OFF);
-    fast_tables_begin<M, PPT>(P.tables, tab, ctx);
-    constexpr int NBLK = M / CB;
+    const cplx* tile = reinterpret_cast<const cplx*>(smem_raw + S::TILE_OFF);
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + S::BAR_OFF);
+    for (int i = ctx.tid(); i < S::NTAB_PAD / 2; i += ctx.bdim()) ctx.cp_async16(tab + 2 * i, P.tables_c + 2 * i);
+    constexpr int NBLK = M / CBT;
     const int rc = ctx.bx() / NBLK;
+    const int kc0 = (ctx.bx() - rc * NBLK) * CBT;
     if (ctx.tid() == 0) {
         ctx.mbar_init(bar, 1);
-        TileCtl* ctl = reinterpret_cast<TileCtl*>(smem_raw + F::COL_BAR_OFF + 16);
+        TileCtl* ctl = reinterpret_cast<TileCtl*>(smem_raw + S::BAR_OFF + 16);
         ctl->next_row = (int)P.row_begin + rc * P.Sr;
         ctl->rows_per_tile = 2 * P.Sr;
         ctl->remaining = P.batch;
-        ctl->col = (ctx.bx() - rc * NBLK) * CB;
+        ctl->col = kc0;
     }
-    const int half = ctx.tid() / F::COL_HALF;
-    const int th = ctx.tid() - half * F::COL_HALF;
-    const int col = th % CB;
-    const int g = th / CB;
-    cplx* ex = smem + F::NTAB_PAD + (size_t)half * (CB * F::Sh::SMEM_ELEMS) + col;
+    const int half = ctx.tid() / S::HALF;
+    const int th = ctx.tid() - half * S::HALF;
+    const int col = th % CBT;
+    const int g = th / CBT;
+    cplx* ex = smem + S::NTAB_PAD + (size_t)half * (CBT * F::Sh::SMEM_ELEMS) + col;
     const int rr = half;
-    const SmemTw<M, PPT> tw{tab};
+    const TmaTw<M, PPT, CBT> tw{tab};
     const GroupSync<Ctx, 2> gs{ctx, 0, 0};
-    const TileHook<Ctx> hook{ctx, smem_raw, &P, F::COL_TILE_OFF, F::COL_BAR_OFF};
+    const TileHook<Ctx> hook{ctx, smem_raw, &P, S::TILE_OFF, S::BAR_OFF, M * CBT};
 
-    float* dst = P.ic + ((size_t)(rr * 2 + rc) * M + g) * M + (ctx.bx() - rc * NBLK) * CB + col;
+    float* dst = P.ic + ((size_t)(rr * 2 + rc) * M + g) * M + kc0 + col;
     float acc[PPT];
 #pragma unroll
     for (int e = 0; e < PPT; ++e) acc[e] = dst[(size_t)(TG * e) * M];
@@ -424,21 +465,28 @@ LITHO_HD void fast_cols_tma_body(const FastColsParams& P, const Ctx& ctx, unsign
         cplx v[PPT];
         if (last >= M - 1) {
 #pragma unroll
-            for (int e = 0; e < PPT; ++e) v[e] = tile[th + e * (TG * CB)];
+            for (int e = 0; e < PPT; ++e) v[e] = tile[th + e * (TG * CBT)];
         } else {
 #pragma unroll
             for (int e = 0; e < PPT; ++e) {  // rows past Sr hold stale (finite or not) data: select, never multiply
-                const cplx x = tile[th + e * (TG * CB)];
+                const cplx x = tile[th + e * (TG * CBT)];
                 const bool in = g + TG * e <= last;
                 v[e] = mk(in ? x.x : 0.f, in ? x.y : 0.f);
             }
         }
-        if (rr) {
+        if (rr) {  // pre-twiddle w_2M^u, u = g + TG*e; u > M/2 from the mirrored entry: w^u = -conj(w^(M-u))
 #pragma unroll
-            for (int e = 0; e < PPT; ++e) v[e] = cmul(v[e], tab[F::PRE_OFF + g + TG * e]);
+            for (int e = 0; e < PPT; ++e) {
+                if (TG * e + TG - 1 <= M / 2) {
+                    v[e] = cmul(v[e], tab[g + TG * e]);
+                } else {  // u >= M/2 (M/2 is a multiple of TG): index M-u is in [0, M/2]
+                    const cplx t = tab[M - TG * e - g];
+                    v[e] = cmul(v[e], mk(-t.x, t.y));
+                }
+            }
         }
         if (P.Sr > M) {  // rim input u = M folds onto slot 0 with w_2M^(rr*M) = (-1)^rr
-            const cplx y = tile[M * CB + col];
+            const cplx y = tile[M * CBT + col];
             const float sgn = (g == 0) ? (rr ? -1.f : 1.f) : 0.f;
             v[0] = mk(v[0].x + sgn * y.x, v[0].y + sgn * y.y);
         }
@@ -446,7 +494,7 @@ LITHO_HD void fast_cols_tma_body(const FastColsParams& P, const Ctx& ctx, unsign
             ctx.sync();
             hook.after_first_sync();
         }
-        fft_run<M, PPT, false>(v, ex, CB, g, tw, gs, hook);
+        fft_run<M, PPT, false>(v, ex, CBT, g, tw, gs, hook);
         const float w = P.weights ? P.weights[P.s_begin + sl] : 1.f;
 #pragma unroll
         for (int e = 0; e < PPT; ++e) acc[e] += w * cnorm2(v[e]);

@@ -158,15 +158,20 @@ struct DevCtx {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // Issued by ONE thread: announce `bytes` on the barrier, then copy `nbox` boxes of the tile whose first
-    // element is (row, col) into consecutive box-sized pieces of `smem_dst` (128-byte aligned).
-    __device__ __forceinline__ void tile_load(void* smem_dst, const TileMap& tm, int row, int col, int nbox,
+    // Issued by ONE thread: announce the bytes on the barrier, then copy `nbox` boxes of the tile whose first
+    // element is (row, col) into consecutive box-sized pieces of `smem_dst` (128-byte aligned) and, if
+    // rim_elem >= 0, the single row that follows the boxes (row + nbox*box_rows) to element rim_elem of the
+    // buffer with a 1-D bulk copy.
+    __device__ __forceinline__ void tile_load(void* smem_dst, const TileMap& tm, int row, int col, int nbox, int rim_elem,
                                               unsigned long long* bar) const {
         const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
         const unsigned box_bytes = (unsigned)(tm.box_rows * tm.box_cols) * 8u;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(box_bytes * (unsigned)nbox)
+        const unsigned rim_bytes = rim_elem >= 0 ? (unsigned)tm.box_cols * 8u : 0u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b),
+                     "r"(box_bytes * (unsigned)nbox + rim_bytes)
                      : "memory");
-        unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+        const unsigned d0 = (unsigned)__cvta_generic_to_shared(smem_dst);
+        unsigned d = d0;
         const unsigned long long mp = reinterpret_cast<unsigned long long>(tm.map);
 #pragma unroll 1
         for (int i = 0; i < nbox; ++i) {
@@ -177,6 +182,12 @@ struct DevCtx {
                 ::"r"(d), "l"(mp), "r"(x), "r"(y), "r"(b)
                 : "memory");
             d += box_bytes;
+        }
+        if (rim_elem >= 0) {
+            const cplx* src = tm.base + (long long)(row + nbox * tm.box_rows) * tm.pitch + col;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(d0 + (unsigned)rim_elem * 8u), "l"(src), "r"(rim_bytes), "r"(b)
+                         : "memory");
         }
     }
     // All threads: wait until the copy announced for this phase has landed.  Bounded: a logic error gives

@@ -111,13 +111,43 @@ abbe_fast_cols_kernel(const __grid_constant__ FastColsParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     fast_cols_body<M, PPT>(P, DevCtx{}, reinterpret_cast<cplx*>(smem_raw));
 }
-template <int M, int PPT>
-__global__ void __launch_bounds__(FastShape<M, PPT>::COL_THREADS, FastShape<M, PPT>::COL_MIN_BLOCKS)
+template <int M, int PPT, int CBT>
+__global__ void __launch_bounds__(TmaShape<M, PPT, CBT>::THREADS, TmaShape<M, PPT, CBT>::MIN_BLOCKS)
 abbe_fast_cols_tma_kernel(const __grid_constant__ FastColsParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw_tma[];
-    if constexpr (FastShape<M, PPT>::COL_TMA) fast_cols_tma_body<M, PPT>(P, DevCtx{}, smem_raw_tma);
+    fast_cols_tma_body<M, PPT, CBT>(P, DevCtx{}, smem_raw_tma);
 }
 #endif
+
+// wide / narrow tile widths of the TMA-staged column kernel for this M (0: none)
+template <int M, int PPT>
+struct TmaWidths {
+    using F = FastShape<M, PPT>;
+    static constexpr int WIDE_C = F::CB_DUAL >= 2 ? F::CB_DUAL : 2;
+    static constexpr int WIDE = (F::CB_DUAL >= 2 && TmaShape<M, PPT, WIDE_C>::OK) ? WIDE_C : 0;
+    // the narrow tile only pays when two CTAs then fit an SM
+    static constexpr int NARROW_C = F::CB_DUAL / 2 >= 2 ? F::CB_DUAL / 2 : 2;
+    static constexpr int NARROW = (F::CB_DUAL / 2 >= 2 && TmaShape<M, PPT, NARROW_C>::OK &&
+                                   TmaShape<M, PPT, NARROW_C>::MIN_BLOCKS == 2) ? NARROW_C : 0;
+};
+
+template <int M, int PPT, int CBT>
+int launch_fast_cols_tma(const FastColsParams& P, litho_stream_t st) {
+    using S = TmaShape<M, PPT, CBT>;
+    const int gx = 2 * (M / CBT);
+#if defined(LITHO_EMU)
+    (void)st;
+    litho_emu::launch(gx, 1, 1, S::THREADS, S::SMEM, [&](const litho_emu::EmuCtx& c, char* s) {
+        fast_cols_tma_body<M, PPT, CBT>(P, c, (unsigned char*)s);
+    });
+    return 0;
+#else
+    int e = set_smem(abbe_fast_cols_tma_kernel<M, PPT, CBT>, S::SMEM);
+    if (e) return e;
+    abbe_fast_cols_tma_kernel<M, PPT, CBT><<<dim3(gx, 1, 1), dim3(S::THREADS, 1, 1), S::SMEM, st>>>(P);
+    return (int)cudaGetLastError();
+#endif
+}
 
 template <int M, int PPT>
 int launch_fast_rows_m(const FastRowsParams& P, int gx, litho_stream_t st) {
@@ -139,27 +169,22 @@ template <int M, int PPT>
 int launch_fast_cols_m(const FastColsParams& P, litho_stream_t st) {
     using F = FastShape<M, PPT>;
     const int gx = 2 * (M / F::CB);
-    if (P.use_tma && !F::COL_TMA) return -2;
+    if (P.use_tma) {  // P.use_tma = columns per tile
+        using W = TmaWidths<M, PPT>;
+        if constexpr (W::WIDE > 0) {
+            if (P.use_tma == W::WIDE) return launch_fast_cols_tma<M, PPT, W::WIDE>(P, st);
+        }
+        if constexpr (W::NARROW > 0) {
+            if (P.use_tma == W::NARROW) return launch_fast_cols_tma<M, PPT, W::NARROW>(P, st);
+        }
+        return -2;
+    }
 #if defined(LITHO_EMU)
     (void)st;
-    if constexpr (F::COL_TMA) {
-        if (P.use_tma) {
-            litho_emu::launch(gx, 1, 1, F::COL_THREADS, F::COL_SMEM_TMA, [&](const litho_emu::EmuCtx& c, char* s) {
-                fast_cols_tma_body<M, PPT>(P, c, (unsigned char*)s);
-            });
-            return 0;
-        }
-    }
     litho_emu::launch(gx, F::COL_GRID_Y, 1, F::COL_THREADS, F::COL_SMEM,
                       [&](const litho_emu::EmuCtx& c, char* s) { fast_cols_body<M, PPT>(P, c, (cplx*)s); });
     return 0;
 #else
-    if (P.use_tma) {
-        int e = set_smem(abbe_fast_cols_tma_kernel<M, PPT>, F::COL_SMEM_TMA);
-        if (e) return e;
-        abbe_fast_cols_tma_kernel<M, PPT><<<dim3(gx, 1, 1), dim3(F::COL_THREADS, 1, 1), F::COL_SMEM_TMA, st>>>(P);
-        return (int)cudaGetLastError();
-    }
     int e = set_smem(abbe_fast_cols_kernel<M, PPT>, F::COL_SMEM);
     if (e) return e;
     abbe_fast_cols_kernel<M, PPT><<<dim3(gx, F::COL_GRID_Y, 1), dim3(F::COL_THREADS, 1, 1), F::COL_SMEM, st>>>(P);
@@ -171,10 +196,18 @@ template <int M, int PPT>
 int fast_ntab_m() {
     return FastShape<M, PPT>::NTAB;
 }
-// columns per TMA-staged tile (0: shape has no TMA-staged column kernel)
+// TMA-staged column kernel of this M: which = 0 wide tile width, 1 narrow tile width (0: not available),
+// 2 rows per TMA box, 3 element count of the compact twiddle table
 template <int M, int PPT>
-int fast_tma_cols_m() {
-    return FastShape<M, PPT>::COL_TMA ? FastShape<M, PPT>::CB : 0;
+int fast_tma_cols_m(int which) {
+    using W = TmaWidths<M, PPT>;
+    using S = TmaShape<M, PPT, (W::WIDE > 0 ? W::WIDE : 2)>;
+    switch (which) {
+        case 0: return W::WIDE;
+        case 1: return W::NARROW;
+        case 2: return S::BOX_ROWS;
+        default: return S::NTAB_PAD;
+    }
 }
 
 #if LITHO_INST_M >= 512 && LITHO_INST_M <= 2048
@@ -214,12 +247,12 @@ template int launch_fast_fused_m<LITHO_INST_M>(const FusedParams&, int, litho_st
 template int launch_fast_rows_m<LITHO_INST_M, 32>(const FastRowsParams&, int, litho_stream_t);
 template int launch_fast_cols_m<LITHO_INST_M, 32>(const FastColsParams&, litho_stream_t);
 template int fast_ntab_m<LITHO_INST_M, 32>();
-template int fast_tma_cols_m<LITHO_INST_M, 32>();
+template int fast_tma_cols_m<LITHO_INST_M, 32>(int);
 #if defined(LITHO_WITH_PPT16)  // 16 points per thread: measured 2x slower on B200 (profiles/README.md), not built by default
 template int launch_fast_rows_m<LITHO_INST_M, 16>(const FastRowsParams&, int, litho_stream_t);
 template int launch_fast_cols_m<LITHO_INST_M, 16>(const FastColsParams&, litho_stream_t);
 template int fast_ntab_m<LITHO_INST_M, 16>();
-template int fast_tma_cols_m<LITHO_INST_M, 16>();
+template int fast_tma_cols_m<LITHO_INST_M, 16>(int);
 #endif
 #endif
 

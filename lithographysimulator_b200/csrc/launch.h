@@ -35,7 +35,7 @@ int launch_fast_cols_m(const FastColsParams& P, litho_stream_t st);
 template <int M, int PPT>
 int fast_ntab_m();
 template <int M, int PPT>
-int fast_tma_cols_m();
+int fast_tma_cols_m(int which);
 // fused persistent kernel (fast_fused_body), instantiated for M = 512, 1024, 2048
 template <int M>
 int launch_fast_fused_m(const FusedParams& P, int gx, litho_stream_t st);

@@ -320,6 +320,10 @@ static int make_tile_map(TileMap* tm, const void* base, int M, long long rows, i
 // --------------------------------------------------------------------------- plan
 // T ring slots of the fast path: rows(b) may run LITHO_TSLOTS-1 batches ahead of cols(b)
 #define LITHO_TSLOTS 3
+// TMA-staged column pass: narrow tiles (two 256-thread CTAs per SM) or wide ones (one 512-thread CTA)
+#ifndef LITHO_DEFAULT_COL_NARROW
+#define LITHO_DEFAULT_COL_NARROW 1
+#endif
 struct litho_plan {
     int pn, N;
     int bbox[4];
@@ -337,6 +341,8 @@ struct litho_plan {
     cplx* tables;    // device twiddle tables of the fast kernels (owned by the plan)
     int n_sm;
     int tma_cols;    // > 0: columns per tile of the TMA-staged column kernel (0: plain global loads)
+    int tma_box_rows;  // rows per TMA box (TmaShape::BOX_ROWS)
+    cplx* tables_c;  // device: compact twiddle tables of the TMA-staged column kernel (owned by the plan)
     // T ring bookkeeping across accumulate calls (LITHO_PHASE_INPUTS_READY): which ring the ev_cols events of
     // the last call refer to
     mutable const void* last_ws;
@@ -386,12 +392,12 @@ static int dispatch_fast_fused(int M, const FusedParams& P, int gx, litho_stream
     }
     return -1;
 }
-static int dispatch_fast_tma_cols(int M, int ppt) {
+static int dispatch_fast_tma_cols(int M, int ppt, int which) {
     switch (M) {
 #if defined(LITHO_WITH_PPT16)
-#define X(m) case m: return ppt == 16 ? fast_tma_cols_m<m, 16>() : fast_tma_cols_m<m, 32>();
+#define X(m) case m: return ppt == 16 ? fast_tma_cols_m<m, 16>(which) : fast_tma_cols_m<m, 32>(which);
 #else
-#define X(m) case m: return fast_tma_cols_m<m, 32>();
+#define X(m) case m: return fast_tma_cols_m<m, 32>(which);
 #endif
         LITHO_FOR_EACH_FAST_M(X)
 #undef X
@@ -610,7 +616,7 @@ int litho_plan_create_ex(int pn, int N, const int* bbox, int flags, litho_plan_t
     }
     size_t per = (size_t)p->zp.R * p->Sr * p->zp.Wr * sizeof(cplx);
     // ---- fast path eligibility: even window fit S <= Mf+1, coarse grid Nc = 2*Mf no finer than N ----
-    p->path = 1; p->tables = nullptr; p->Mf = p->Nc = p->q = 0; p->rim_row = p->rim_col = 0;
+    p->path = 1; p->tables = nullptr; p->tables_c = nullptr; p->tma_box_rows = 0; p->Mf = p->Nc = p->q = 0; p->rim_row = p->rim_col = 0;
     p->fused = 0; p->fused_B = 2; p->counters = nullptr; p->counters_cap = 0; p->tma_cols = 0;
     p->last_ws = nullptr; p->last_batch = 0;
     for (int i = 0; i < LITHO_TSLOTS; ++i) p->cols_recorded[i] = 0;
@@ -686,10 +692,40 @@ int litho_plan_create_ex(int pn, int N, const int* bbox, int flags, litho_plan_t
             }
         }
         p->path = 2; p->Mf = Mf; p->Nc = 2 * Mf; p->q = N / (2 * Mf);
-        // TMA-staged column kernel where the shape has one (M <= 1024); LITHO_TMA=0 selects plain loads
-        p->tma_cols = dispatch_fast_tma_cols(Mf, p->ppt);
-        if (const char* env = getenv("LITHO_TMA")) {
-            if (atoi(env) == 0) p->tma_cols = 0;
+        // TMA-staged column kernel where the shape has one (M <= 1024).  LITHO_TMA=0 selects plain loads,
+        // LITHO_COL_NARROW=0/1 the wide (one 512-thread CTA per SM) or narrow (two 256-thread CTAs) tile.
+        {
+            int narrow = LITHO_DEFAULT_COL_NARROW;
+            if (const char* env = getenv("LITHO_COL_NARROW")) narrow = atoi(env) != 0;
+            const int wide_c = dispatch_fast_tma_cols(Mf, p->ppt, 0), narrow_c = dispatch_fast_tma_cols(Mf, p->ppt, 1);
+            p->tma_cols = (narrow && narrow_c > 0) ? narrow_c : wide_c;
+            p->tma_box_rows = dispatch_fast_tma_cols(Mf, p->ppt, 2);
+            if (const char* env = getenv("LITHO_TMA")) {
+                if (atoi(env) == 0) p->tma_cols = 0;
+            }
+        }
+        if (p->tma_cols > 0) {
+            // compact tables: pre[0..M/2] (padded to an even count), then tw1 and tw2 as in the full layout
+            std::vector<cplx> tc(tab.begin(), tab.begin() + Mf / 2 + 1);
+            if (tc.size() & 1) tc.push_back(mk(0.f, 0.f));
+            tc.insert(tc.end(), tab.begin() + Mf + 1, tab.end() - 1);  // (the last entry of tab is its padding)
+            if (tc.size() & 1) tc.push_back(mk(0.f, 0.f));
+            if ((int)tc.size() != dispatch_fast_tma_cols(Mf, p->ppt, 3)) {
+                be_free(p->tables);
+                delete p;
+                return fail(LITHO_ERR_ARG, "plan_create: internal compact table layout mismatch");
+            }
+            rc = be_malloc((void**)&p->tables_c, tc.size() * sizeof(cplx));
+            if (rc == 0) rc = be_h2d(p->tables_c, tc.data(), tc.size() * sizeof(cplx), 0);
+#if !defined(LITHO_EMU)
+            if (rc == 0) rc = (int)cudaStreamSynchronize(0);
+#endif
+            if (rc != 0) {
+                be_free(p->tables);
+                if (p->tables_c) be_free(p->tables_c);
+                delete p;
+                return fail(LITHO_ERR_CUDA, std::string("plan_create: compact tables: ") + be_errstr(rc));
+            }
         }
         p->rim_row = (p->Sr == Mf + 1);
         p->rim_col = (p->Sc == Mf + 1);
@@ -717,6 +753,7 @@ int litho_plan_create_ex(int pn, int N, const int* bbox, int flags, litho_plan_t
 void litho_plan_destroy(litho_plan_t* p) {
     if (!p) return;
     if (p->tables) be_free(p->tables);
+    if (p->tables_c) be_free(p->tables_c);
     if (p->counters) be_free(p->counters);
 #if !defined(LITHO_EMU)
     if (p->aux_stream) {
@@ -923,14 +960,15 @@ int litho_abbe_fft_accumulate_ex(const litho_plan_t* p, const void* maskFT, cons
         for (int i = 0; i < LITHO_TSLOTS; ++i) Tslot[i] = (cplx*)workspace + (size_t)i * slot_elems;
         // one tensor map over the whole ring; a tile = Sr rows x tma_cols columns fetched in nbox boxes
         if (p->tma_cols > 0 && (phases & 2)) {
-            // boxes of <= 256 rows whose byte size is a multiple of 128 (alignment of the TMA destination)
-            int nbox = (p->Sr + 255) / 256;
-            int box_rows = ((p->Sr + nbox - 1) / nbox + 1) & ~1;
-            if (box_rows > 256) { ++nbox; box_rows = ((p->Sr + nbox - 1) / nbox + 1) & ~1; }
-            if (nbox <= 5 && make_tile_map(&fc.tile, workspace, p->Mf, (long long)LITHO_TSLOTS * batch * 2 * p->Sr, box_rows,
+            // <= 4 boxes of M/4 rows cover the rows u < M that exist; the rim row u = M (Sr == M+1) is a 1-D copy
+            const int body = p->Sr > p->Mf ? p->Mf : p->Sr;
+            const int nbox = (body + p->tma_box_rows - 1) / p->tma_box_rows;
+            if (make_tile_map(&fc.tile, workspace, p->Mf, (long long)LITHO_TSLOTS * batch * 2 * p->Sr, p->tma_box_rows,
                               p->tma_cols) == 0) {
-                fc.use_tma = 1;
+                fc.use_tma = p->tma_cols;
                 fc.nbox = nbox;
+                fc.rim = p->Sr > p->Mf;
+                fc.tables_c = p->tables_c;
             }
         }
 #if !defined(LITHO_EMU)
