@@ -65,6 +65,12 @@ int litho_pupil_bbox(const void* pupil, int pn, int* bbox_host, void* stream);
  * extents {cmin,cmax} of the first and last bbox row and {rmin,rmax} of the first and last bbox column
  * (the pupil's rim pixels, which carry the one frequency line the coarse grid aliases).  Synchronises. */
 int litho_pupil_support(const void* pupil, int pn, int* support_host, void* stream);
+/* Same for the `lines` (1..LITHO_RIM_LINES) outermost bbox rows and columns: support_host[4 + 8k ..] = extents of
+ * row r0+k, row r1-k, column c0+k, column c1-k (4 + 8*lines ints in all; an empty line has lo > hi).  The
+ * reference's fp16 pupil grid makes the support pn/2+3 wide at pn = 8192: the fast path then folds the two extra
+ * rows/columns and needs the extents of three lines per side to keep its rim sums cheap. */
+#define LITHO_RIM_LINES 3
+int litho_pupil_support_lines(const void* pupil, int pn, int lines, int* support_host, void* stream);
 
 /* min/max of the source shifts: bounds_host = {d0 min, d0 max, d1 min, d1 max}.  Synchronises.
  * A fast plan (path 2) may only be used when these lie inside plan_info.shift_range. */
@@ -73,9 +79,11 @@ int litho_shift_bounds(const int32_t* shifts, int n_src, int* bounds_host, void*
 /* Plan for abbeImage(fft=True) on a pn x pn grid with FFT-approximation length N.
  * litho_plan_create takes the 4-int bbox; litho_plan_create_ex the 12-int support of
  * litho_pupil_support (cheaper rim sums).  flags: 0 or LITHO_PLAN_GENERIC.
- * Path 2 is chosen when the window fits S <= M+1, M a power of two <= 4096, and 2M <= N. */
+ * litho_plan_create_lines takes the support of litho_pupil_support_lines (lines = 0: bbox only).
+ * Path 2 is chosen when the window fits S <= M + LITHO_RIM_LINES, M a power of two <= 4096, and 2M <= N. */
 int litho_plan_create(int pn, int N, const int* bbox, int flags, litho_plan_t** plan);
 int litho_plan_create_ex(int pn, int N, const int* support, int flags, litho_plan_t** plan);
+int litho_plan_create_lines(int pn, int N, const int* support, int lines, int flags, litho_plan_t** plan);
 void litho_plan_destroy(litho_plan_t* plan);
 int litho_plan_get_info(const litho_plan_t* plan, litho_plan_info_t* info);
 size_t litho_plan_workspace_bytes(const litho_plan_t* plan, int batch);

@@ -25,6 +25,7 @@ class PlanInfo(C.Structure):
                 ("intensity_elems", C.c_uint64), ("shift_range", C.c_int * 4)]
 
 PLAN_GENERIC = 1
+RIM_LINES = 3  # LITHO_RIM_LINES
 PHASE_INPUTS_READY = 4  # litho_abbe_fft_accumulate_ex: inputs valid on the device at call time
 
 
@@ -37,9 +38,11 @@ SYMBOLS = [
     ("litho_epsilon_n", C.c_int, [C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     ("litho_pupil_bbox", C.c_int, [_P, C.c_int, C.POINTER(C.c_int), _P]),
     ("litho_pupil_support", C.c_int, [_P, C.c_int, C.POINTER(C.c_int), _P]),
+    ("litho_pupil_support_lines", C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_int), _P]),
     ("litho_shift_bounds", C.c_int, [_P, C.c_int, C.POINTER(C.c_int), _P]),
     ("litho_plan_create", C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(_P)]),
     ("litho_plan_create_ex", C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(_P)]),
+    ("litho_plan_create_lines", C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(_P)]),
     ("litho_plan_finalize_workspace_bytes", C.c_size_t, [_P]),
     ("litho_plan_destroy", None, [_P]),
     ("litho_plan_get_info", C.c_int, [_P, C.POINTER(PlanInfo)]),
@@ -100,9 +103,10 @@ class NativeLib:
         self.check(self.litho_pupil_bbox(pupil_ptr, pn, box, stream), "litho_pupil_bbox")
         return tuple(box)
 
-    def pupil_support(self, pupil_ptr: int, pn: int, stream: int = 0):
-        sup = (C.c_int * 12)()
-        self.check(self.litho_pupil_support(pupil_ptr, pn, sup, stream), "litho_pupil_support")
+    def pupil_support(self, pupil_ptr: int, pn: int, stream: int = 0, lines: int = RIM_LINES):
+        """bbox + extents of the `lines` outermost rows/columns of the pupil support (4 + 8*lines ints)."""
+        sup = (C.c_int * (4 + 8 * lines))()
+        self.check(self.litho_pupil_support_lines(pupil_ptr, pn, lines, sup, stream), "litho_pupil_support_lines")
         return tuple(sup)
 
     def shift_bounds(self, shifts_ptr, n_src: int, stream: int = 0):
@@ -111,14 +115,14 @@ class NativeLib:
         return tuple(b)
 
     def plan_create(self, pn: int, N: int, support, flags: int = 0) -> "Plan":
-        """`support` is the 4-int bbox or the 12-int result of pupil_support()."""
+        """`support` is the 4-int bbox or the (4 + 8*lines)-int result of pupil_support()."""
         handle = _P()
-        if len(support) == 12:
-            arr = (C.c_int * 12)(*support)
-            self.check(self.litho_plan_create_ex(pn, N, arr, flags, C.byref(handle)), "litho_plan_create_ex")
-        else:
-            arr = (C.c_int * 4)(*support)
-            self.check(self.litho_plan_create(pn, N, arr, flags, C.byref(handle)), "litho_plan_create")
+        n = len(support)
+        if n < 4 or (n - 4) % 8:
+            raise LithoError(f"plan_create: support must hold 4 + 8*lines ints, got {n}")
+        arr = (C.c_int * n)(*support)
+        self.check(self.litho_plan_create_lines(pn, N, arr, (n - 4) // 8, flags, C.byref(handle)),
+                   "litho_plan_create_lines")
         return Plan(self, handle)
 
 

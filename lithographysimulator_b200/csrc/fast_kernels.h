@@ -27,6 +27,16 @@ namespace litho {
 
 LITHO_HD int iclamp(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
+// The window may exceed the even fit S = M+1 by up to RIM_EXTRA inputs per axis (S <= M + 1 + RIM_EXTRA): the
+// reference's fp16 pupil grid gives S = pn/2 + 3 at pn = 8192.  Inputs u = M .. S-1 fold onto slots u - M of the
+// length-M transforms, and the frequency lines |d| = M .. S-1 of sum_s |E_s|^2, which alias on the coarse grid,
+// are carried separately by rim_body (RIM_LINES of them per axis at most).
+#ifndef LITHO_RIM_EXTRA
+#define LITHO_RIM_EXTRA 2
+#endif
+constexpr int RIM_EXTRA = LITHO_RIM_EXTRA;
+constexpr int RIM_LINES = RIM_EXTRA + 1;
+
 template <int M, int PPT>
 struct FastShape {
     using Sh = FftShape<M, PPT>;
@@ -117,7 +127,7 @@ struct FastColsParams {
     // TMA-staged variant: T seen as one 2-D tensor (rows of M complex elements) starting at tile.base;
     // row_begin = row of T[sl = 0][rc = 0][u = 0] of this launch in that tensor; nbox boxes per tile
     // TMA-staged variant (fast_cols_tma_body): use_tma = columns per tile (0: plain loads)
-    int use_tma, nbox, rim;      // boxes per tile; rim: the tile has the extra row u = M (Sr == M+1)
+    int use_tma, nbox, rim;      // boxes per tile; rim: rows u = M .. Sr-1 of the tile (0 .. RIM_LINES), 1-D copies
     long long row_begin;
     const cplx* tables_c;        // compact twiddle tables (TmaShape layout)
     TileMap tile;
@@ -190,14 +200,19 @@ LITHO_HD void fast_row_load(cplx (&v)[PPT], const FastRowsParams& P, int s, int 
             }
         }
     }
+    // inputs u = M .. Sc-1 fold onto slots u - M with w_2M^(r*M) = (-1)^r; the slot's pre-twiddle follows
+    if (P.Sc > M) {
+#pragma unroll
+        for (int k = 0; k <= RIM_EXTRA; ++k) {
+            if (k < P.Sc - M && g == k % TG) {
+                const cplx y = cmul(ldg_c(prow + M + k), ldg_c(mrow + M + k));
+                v[k / TG] = r ? csub(v[k / TG], y) : cadd(v[k / TG], y);
+            }
+        }
+    }
     if (r) {
 #pragma unroll
         for (int e = 0; e < PPT; ++e) v[e] = cmul(v[e], tab[F::PRE_OFF + g + TG * e]);
-    }
-    if (P.Sc > M) {  // rim input u = M folds onto slot 0 with w_2M^(r*M) = (-1)^r
-        const cplx y = cmul(ldg_c(prow + M), ldg_c(mrow + M));
-        const float sgn = (g == 0) ? (r ? -1.f : 1.f) : 0.f;
-        v[0] = mk(v[0].x + sgn * y.x, v[0].y + sgn * y.y);
     }
 }
 
@@ -227,14 +242,18 @@ template <int M, int PPT, bool CG>
 LITHO_HD void fast_col_finish(cplx (&v)[PPT], const cplx* src, int Sr, int rr, int g, const cplx* tab) {
     using F = FastShape<M, PPT>;
     constexpr int TG = F::TG;
+    if (Sr > M) {  // rows u = M .. Sr-1 fold onto slots u - M with (-1)^rr, before the slot's pre-twiddle
+#pragma unroll
+        for (int k = 0; k <= RIM_EXTRA; ++k) {
+            if (k < Sr - M && g == k % TG) {
+                const cplx y = CG ? ldcg_c(src + (size_t)(M + k) * M) : ldg_c(src + (size_t)(M + k) * M);
+                v[k / TG] = rr ? csub(v[k / TG], y) : cadd(v[k / TG], y);
+            }
+        }
+    }
     if (rr) {
 #pragma unroll
         for (int e = 0; e < PPT; ++e) v[e] = cmul(v[e], tab[F::PRE_OFF + g + TG * e]);
-    }
-    if (Sr > M) {
-        const cplx y = CG ? ldcg_c(src + (size_t)M * M) : ldg_c(src + (size_t)M * M);
-        const float sgn = (g == 0) ? (rr ? -1.f : 1.f) : 0.f;
-        v[0] = mk(v[0].x + sgn * y.x, v[0].y + sgn * y.y);
     }
 }
 
@@ -363,7 +382,7 @@ struct TmaShape {
     static constexpr int BOX_ROWS = M / 4 > 256 ? 256 : M / 4;     // rows per TMA box (<= 4 boxes cover u < M)
     static constexpr size_t EX_BYTES = (size_t)2 * CBT * Sh::SMEM_ELEMS * sizeof(cplx);
     static constexpr size_t TILE_OFF = ((size_t)NTAB_PAD * sizeof(cplx) + EX_BYTES + 127) / 128 * 128;
-    static constexpr size_t TILE_BYTES = ((size_t)(M + 1) * CBT * sizeof(cplx) + 15) / 16 * 16;
+    static constexpr size_t TILE_BYTES = ((size_t)(M + 1 + RIM_EXTRA) * CBT * sizeof(cplx) + 15) / 16 * 16;
     static constexpr size_t BAR_OFF = TILE_OFF + TILE_BYTES;
     static constexpr size_t SMEM = BAR_OFF + 48;  // mbarrier (8, padded to 16) + TileCtl
     // a box must be a multiple of 128 bytes (TMA destination alignment) and a half at least one warp... no: the
@@ -410,7 +429,7 @@ struct TileHook {
             const int rem = ctl->remaining;
             if (rem > 0) {
                 const int row = ctl->next_row;
-                ctx.tile_load(smem_raw + tile_off, P->tile, row, ctl->col, P->nbox, P->rim ? rim_elem : -1,
+                ctx.tile_load(smem_raw + tile_off, P->tile, row, ctl->col, P->nbox, P->rim, rim_elem,
                               reinterpret_cast<unsigned long long*>(smem_raw + bar_off));
                 ctl->next_row = row + ctl->rows_per_tile;
                 ctl->remaining = rem - 1;
@@ -474,6 +493,15 @@ LITHO_HD void fast_cols_tma_body(const FastColsParams& P, const Ctx& ctx, unsign
                 v[e] = mk(in ? x.x : 0.f, in ? x.y : 0.f);
             }
         }
+        if (P.Sr > M) {  // rim rows u = M .. Sr-1 fold onto slots u - M with (-1)^rr, before the slot's pre-twiddle
+#pragma unroll
+            for (int k = 0; k <= RIM_EXTRA; ++k) {
+                if (k < P.Sr - M && g == k % TG) {
+                    const cplx y = tile[(M + k) * CBT + col];
+                    v[k / TG] = rr ? csub(v[k / TG], y) : cadd(v[k / TG], y);
+                }
+            }
+        }
         if (rr) {  // pre-twiddle w_2M^u, u = g + TG*e; u > M/2 from the mirrored entry: w^u = -conj(w^(M-u))
 #pragma unroll
             for (int e = 0; e < PPT; ++e) {
@@ -484,11 +512,6 @@ LITHO_HD void fast_cols_tma_body(const FastColsParams& P, const Ctx& ctx, unsign
                     v[e] = cmul(v[e], mk(-t.x, t.y));
                 }
             }
-        }
-        if (P.Sr > M) {  // rim input u = M folds onto slot 0 with w_2M^(rr*M) = (-1)^rr
-            const cplx y = tile[M * CBT + col];
-            const float sgn = (g == 0) ? (rr ? -1.f : 1.f) : 0.f;
-            v[0] = mk(v[0].x + sgn * y.x, v[0].y + sgn * y.y);
         }
         if constexpr (F::Sh::NP == 1) {  // single-pass FFT: no exchange, hence no barrier inside fft_run
             ctx.sync();
@@ -660,12 +683,14 @@ LITHO_HD void fast_fused_body(const FusedParams& P, const Ctx& ctx, cplx* smem, 
 }
 
 // ----------------------------------------------------------------------------- rim lines
-// Frow[n + M] += sum_s w_s sum_{v1 - v2 = n} G_s[Sr-1][v1] * conj(G_s[0][v2])      (needs Sr == M+1)
-// Fcol[m + M] += sum_s w_s sum_{u1 - u2 = m} G_s[u1][Sc-1] * conj(G_s[u2][0])      (needs Sc == M+1)
-// These are the Fourier coefficients of sum_s |E_s|^2 at frequency +M along the row / column axis,
-// the only ones the Nc = 2M coarse grid cannot tell from their -M partners.
-// `ext` = non-zero extents of the pupil's first/last window row and column:
-//   {top_lo, top_hi, bot_lo, bot_hi, left_lo, left_hi, right_lo, right_hi}  (window coordinates)
+// F[d1][d2] = sum_s w_s sum_{u1-u2=d1, v1-v2=d2} G_s[u1][v1] conj(G_s[u2][v2]) are the Fourier coefficients of
+// sum_s |E_s|^2.  Those with |d1| >= M or |d2| >= M alias on the Nc = 2M coarse grid; they only involve the few
+// window rows (columns) within er = Sr-1-M (ec = Sc-1-M) of the edges, so they are summed directly here:
+//   frow[k][n + Sc-1] = F[M+k][n],  k = 0..er, n = -(Sc-1)..Sc-1   (row pairs u2 = t, u1 = t + M + k, t = 0..er-k)
+//   fcol[k][m + Sr-1] = F[m][M+k],  k = 0..ec, m = -(Sr-1)..Sr-1   (column pairs likewise)
+// Negative frequencies follow from F[-d] = conj(F[d]).  `ext` = non-zero extents of the pupil along each of
+// those lines (window coordinates), so that only the populated stretch is correlated:
+//   ext[0][k] top row k, ext[1][k] bottom row Sr-1-k, ext[2][k] left column k, ext[3][k] right column Sc-1-k.
 struct RimParams {
     const cplx* pupil;
     const cplx* mask;
@@ -673,10 +698,10 @@ struct RimParams {
     const int2_* shifts;
     const float* weights;
     int n_src;
-    int ext[8];
-    int do_row, do_col;
-    float* frow;  // (2M+1) complex, interleaved
-    float* fcol;
+    int ext[4][RIM_LINES][2];
+    int er, ec;     // -1: no rim lines on that axis
+    float* frow;    // [er+1][2*Sc-1] complex, interleaved
+    float* fcol;    // [ec+1][2*Sr-1] complex
 };
 
 LITHO_HD void atomic_add_f(float* p, float v) {
@@ -687,80 +712,108 @@ LITHO_HD void atomic_add_f(float* p, float v) {
 #endif
 }
 
-// one CTA per source point; smem holds the two rim vectors (<= 2*(M+1) elements)
+// one CTA per source point; smem holds the two vectors of the pair being correlated
 template <class Ctx>
 LITHO_HD void rim_body(const RimParams& P, const Ctx& ctx, cplx* smem) {
     const int s = ctx.bx();
     const int2_ sh = P.shifts[s];
     const float w = P.weights ? P.weights[s] : 1.f;
     for (int axis = 0; axis < 2; ++axis) {
-        if (axis == 0 ? !P.do_row : !P.do_col) continue;
-        // "hi" vector: last window row (axis 0) / last window column (axis 1); "lo": first
-        const int hl = P.ext[axis * 4 + 2], hh = P.ext[axis * 4 + 3];  // bottom / right extents
-        const int ll = P.ext[axis * 4 + 0], lh = P.ext[axis * 4 + 1];  // top / left extents
-        const int nh = hh - hl + 1, nl = lh - ll + 1;
-        cplx* gh = smem;
-        cplx* gl = smem + nh;
-        ctx.sync();
-        for (int i = ctx.tid(); i < nh + nl; i += ctx.bdim()) {
-            const bool hi = i < nh;
-            const int t = hi ? hl + i : ll + (i - nh);            // position along the vector
-            const int fix = hi ? (axis == 0 ? P.Sr - 1 : P.Sc - 1) : 0;  // the fixed window coordinate
-            const int u = axis == 0 ? fix : t;                     // window row
-            const int v = axis == 0 ? t : fix;                     // window column
-            const cplx p = P.pupil[(size_t)(P.pr0 + u) * P.pn + P.pc0 + v];
-            const cplx m = P.mask[(size_t)iclamp(P.pr0 + u + sh.x, 0, P.pn - 1) * P.pn +
-                                  iclamp(P.pc0 + v + sh.y, 0, P.pn - 1)];
-            smem[i] = cmul(p, m);
-        }
-        ctx.sync();
-        // correlation lags n = (hl + a) - (ll + b), a in [0,nh), b in [0,nl)
-        const int nlag = nh + nl - 1;
+        const int e = axis == 0 ? P.er : P.ec;
+        const int Sfix = axis == 0 ? P.Sr : P.Sc;      // size along the axis the pair is separated on
+        const int Slag = axis == 0 ? P.Sc : P.Sr;      // size along the lines
         float* F = axis == 0 ? P.frow : P.fcol;
-        for (int li = ctx.tid(); li < nlag; li += ctx.bdim()) {
-            const int d = li - (nl - 1);  // a - b
-            const int b0 = d < 0 ? -d : 0;
-            const int b1 = (nh - d) < nl ? (nh - d) : nl;
-            cplx acc = mk(0.f, 0.f);
-            for (int b = b0; b < b1; ++b) acc = cadd(acc, cmul(gh[b + d], cconj(gl[b])));
-            const int n = (hl - ll) + d;
-            atomic_add_f(F + 2 * (n + P.M), w * acc.x);
-            atomic_add_f(F + 2 * (n + P.M) + 1, w * acc.y);
+        for (int k = 0; k <= e; ++k) {                 // frequency M + k
+            for (int t = 0; t + k <= e; ++t) {         // pair: "lo" line t, "hi" line t + M + k = Sfix-1-b
+                const int b = e - k - t;
+                const int ll = P.ext[axis * 2][t][0], lh = P.ext[axis * 2][t][1];
+                const int hl = P.ext[axis * 2 + 1][b][0], hh = P.ext[axis * 2 + 1][b][1];
+                const int nl = lh - ll + 1, nh = hh - hl + 1;
+                if (nl <= 0 || nh <= 0) continue;
+                cplx* gh = smem;
+                cplx* gl = smem + nh;
+                ctx.sync();
+                for (int i = ctx.tid(); i < nh + nl; i += ctx.bdim()) {
+                    const bool hi = i < nh;
+                    const int along = hi ? hl + i : ll + (i - nh);     // position along the line
+                    const int fix = hi ? Sfix - 1 - b : t;             // the line's index on the other axis
+                    const int u = axis == 0 ? fix : along;             // window row
+                    const int v = axis == 0 ? along : fix;             // window column
+                    const cplx p = P.pupil[(size_t)(P.pr0 + u) * P.pn + P.pc0 + v];
+                    const cplx m = P.mask[(size_t)iclamp(P.pr0 + u + sh.x, 0, P.pn - 1) * P.pn +
+                                          iclamp(P.pc0 + v + sh.y, 0, P.pn - 1)];
+                    smem[i] = cmul(p, m);
+                }
+                ctx.sync();
+                // correlation lags n = (hl + a) - (ll + c), a in [0,nh), c in [0,nl)
+                const int nlag = nh + nl - 1;
+                float* Fk = F + (size_t)2 * k * (2 * Slag - 1);
+                for (int li = ctx.tid(); li < nlag; li += ctx.bdim()) {
+                    const int d = li - (nl - 1);  // a - c
+                    const int c0 = d < 0 ? -d : 0;
+                    const int c1 = (nh - d) < nl ? (nh - d) : nl;
+                    cplx acc = mk(0.f, 0.f);
+                    for (int c = c0; c < c1; ++c) acc = cadd(acc, cmul(gh[c + d], cconj(gl[c])));
+                    const int n = (hl - ll) + d;
+                    atomic_add_f(Fk + 2 * (n + Slag - 1), w * acc.x);
+                    atomic_add_f(Fk + 2 * (n + Slag - 1) + 1, w * acc.y);
+                }
+            }
         }
     }
 }
 
 // ----------------------------------------------------------------------------- coarse -> fine
-// Spectrum assembly: Fhat is the centred Nc x Nc DFT of the coarse intensity (index m+K, K = Nc/2 = M,
-// m in [-K,K)); out is (Nc+1) x (Nc+1) with m,n in [-K,K].  Interior copied; the +-K lines come from
-// the rim sums when they exist, otherwise the (then unaliased) -K bin is split... no energy: zero.
+// Spectrum assembly.  fhat is the centred Nc x Nc DFT of the coarse intensity (index m+K, K = Nc/2 = M, m in
+// [-K,K)): fhat[m][n] = sum of F over all (m', n') congruent to (m, n) modulo Nc.  out is the true spectrum on
+// m in [-K-Er, K+Er], n in [-K-Ec, K+Ec] (Er = max(er,0)): entries with |m| >= K or |n| >= K come from the rim
+// sums, interior entries are fhat minus their aliased partners (which are rim entries).
 struct AssembleParams {
     const cplx* fhat;   // [Nc][Nc]
-    const float* frow;  // F[K][n], n = -K..K
-    const float* fcol;  // F[m][K], m = -K..K
-    int Nc, do_row, do_col;
-    cplx* out;          // [Nc+1][Nc+1]
+    const float* frow;  // [er+1][2*Sc-1]
+    const float* fcol;  // [ec+1][2*Sr-1]
+    int Nc, er, ec, Sr, Sc;
+    cplx* out;          // [Nc+1+2*Er][Nc+1+2*Ec]
 };
 
-LITHO_HD cplx rim_get(const float* f, int idx) { return mk(f[2 * idx], f[2 * idx + 1]); }
+LITHO_HD cplx rim_get(const float* f, size_t idx) { return mk(f[2 * idx], f[2 * idx + 1]); }
+
+// F[m][n] for |m| >= K or |n| >= K (zero outside the extent of the autocorrelation)
+LITHO_HD cplx rim_value(const AssembleParams& P, int m, int n) {
+    const int K = P.Nc / 2;
+    const int am = m < 0 ? -m : m, an = n < 0 ? -n : n;
+    if (am >= K) {
+        const int k = am - K;
+        if (k > P.er || an > P.Sc - 1) return mk(0.f, 0.f);
+        const int nn = m > 0 ? n : -n;
+        const cplx v = rim_get(P.frow, (size_t)k * (2 * P.Sc - 1) + (nn + P.Sc - 1));
+        return m > 0 ? v : cconj(v);
+    }
+    const int k = an - K;
+    if (k > P.ec || am > P.Sr - 1) return mk(0.f, 0.f);
+    const int mm = n > 0 ? m : -m;
+    const cplx v = rim_get(P.fcol, (size_t)k * (2 * P.Sr - 1) + (mm + P.Sr - 1));
+    return n > 0 ? v : cconj(v);
+}
 
 LITHO_HD void assemble_elem(const AssembleParams& P, int i, int j) {
     const int K = P.Nc / 2;
-    const int m = i - K, n = j - K;  // in [-K, K]
-    cplx val = mk(0.f, 0.f);
-    const bool mr = (m == K || m == -K), nr = (n == K || n == -K);
-    if (!mr && !nr) {
-        val = P.fhat[(size_t)i * P.Nc + j];
-    } else if (mr && P.do_row) {
-        // F[K][n] = frow[n];  F[-K][n] = conj(F[K][-n])
-        val = (m == K) ? rim_get(P.frow, n + K) : cconj(rim_get(P.frow, -n + K));
-    } else if (nr && P.do_col) {
-        val = (n == K) ? rim_get(P.fcol, m + K) : cconj(rim_get(P.fcol, -m + K));
+    const int Er = P.er > 0 ? P.er : 0, Ec = P.ec > 0 ? P.ec : 0;
+    const int m = i - K - Er, n = j - K - Ec;
+    const int am = m < 0 ? -m : m, an = n < 0 ? -n : n;
+    cplx val;
+    if (am >= K || an >= K) {
+        val = rim_value(P, m, n);
     } else {
-        // no rim energy on this line: the -K bin of the DFT is exact (and ~0), +K is zero
-        if (m != K && n != K) val = P.fhat[(size_t)i * P.Nc + j];
+        val = P.fhat[(size_t)(m + K) * P.Nc + (n + K)];
+        // aliased partners: m +- Nc, n +- Nc inside the extent
+        const int mp = (m + P.Nc <= K + P.er) ? m + P.Nc : ((m - P.Nc >= -K - P.er) ? m - P.Nc : m);
+        const int np = (n + P.Nc <= K + P.ec) ? n + P.Nc : ((n - P.Nc >= -K - P.ec) ? n - P.Nc : n);
+        if (mp != m) val = csub(val, rim_value(P, mp, n));
+        if (np != n) val = csub(val, rim_value(P, m, np));
+        if (mp != m && np != n) val = csub(val, rim_value(P, mp, np));
     }
-    P.out[(size_t)i * (P.Nc + 1) + j] = val;
+    P.out[(size_t)i * (P.Nc + 1 + 2 * Ec) + j] = val;
 }
 
 }  // namespace litho

@@ -159,16 +159,16 @@ struct DevCtx {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // Issued by ONE thread: announce the bytes on the barrier, then copy `nbox` boxes of the tile whose first
-    // element is (row, col) into consecutive box-sized pieces of `smem_dst` (128-byte aligned) and, if
-    // rim_elem >= 0, the single row that follows the boxes (row + nbox*box_rows) to element rim_elem of the
-    // buffer with a 1-D bulk copy.
-    __device__ __forceinline__ void tile_load(void* smem_dst, const TileMap& tm, int row, int col, int nbox, int rim_elem,
-                                              unsigned long long* bar) const {
+    // element is (row, col) into consecutive box-sized pieces of `smem_dst` (128-byte aligned) and the
+    // `rim_rows` rows that follow the boxes (row + nbox*box_rows + k) to elements rim_elem + k*box_cols of the
+    // buffer with 1-D bulk copies.
+    __device__ __forceinline__ void tile_load(void* smem_dst, const TileMap& tm, int row, int col, int nbox, int rim_rows,
+                                              int rim_elem, unsigned long long* bar) const {
         const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
         const unsigned box_bytes = (unsigned)(tm.box_rows * tm.box_cols) * 8u;
-        const unsigned rim_bytes = rim_elem >= 0 ? (unsigned)tm.box_cols * 8u : 0u;
+        const unsigned rim_bytes = (unsigned)tm.box_cols * 8u;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b),
-                     "r"(box_bytes * (unsigned)nbox + rim_bytes)
+                     "r"(box_bytes * (unsigned)nbox + rim_bytes * (unsigned)rim_rows)
                      : "memory");
         const unsigned d0 = (unsigned)__cvta_generic_to_shared(smem_dst);
         unsigned d = d0;
@@ -183,10 +183,11 @@ struct DevCtx {
                 : "memory");
             d += box_bytes;
         }
-        if (rim_elem >= 0) {
-            const cplx* src = tm.base + (long long)(row + nbox * tm.box_rows) * tm.pitch + col;
+#pragma unroll 1
+        for (int k = 0; k < rim_rows; ++k) {
+            const cplx* src = tm.base + (long long)(row + nbox * tm.box_rows + k) * tm.pitch + col;
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(d0 + (unsigned)rim_elem * 8u), "l"(src), "r"(rim_bytes), "r"(b)
+                         ::"r"(d0 + (unsigned)(rim_elem + k * tm.box_cols) * 8u), "l"(src), "r"(rim_bytes), "r"(b)
                          : "memory");
         }
     }

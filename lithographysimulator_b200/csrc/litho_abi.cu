@@ -105,23 +105,29 @@ struct UnpermParams {
     float* out;
 };
 
-// non-zero extents of the first/last bbox row and column of the pupil (absolute grid indices):
-// ext = {row r0: cmin,cmax | row r1: cmin,cmax | col c0: rmin,rmax | col c1: rmin,rmax}
+// non-zero extents of the outermost `lines` bbox rows and columns of the pupil (absolute grid indices):
+// ext[8k + ..] = {row r0+k: cmin,cmax | row r1-k: cmin,cmax | col c0+k: rmin,rmax | col c1-k: rmin,rmax}
 struct ExtParams {
     const cplx* pupil;
-    int pn, r0, r1, c0, c1;
+    int pn, r0, r1, c0, c1, lines;
     int* ext;
 };
 
 template <class Ctx>
 LITHO_HD void ext_body(const ExtParams& P, const Ctx& ctx) {
-    for (int i = ctx.tid(); i < P.pn; i += ctx.bdim()) {
-        const cplx a = P.pupil[(size_t)P.r0 * P.pn + i], b = P.pupil[(size_t)P.r1 * P.pn + i];
-        const cplx c = P.pupil[(size_t)i * P.pn + P.c0], d = P.pupil[(size_t)i * P.pn + P.c1];
-        if (a.x != 0.f || a.y != 0.f) { atomic_min_i(P.ext + 0, i); atomic_max_i(P.ext + 1, i); }
-        if (b.x != 0.f || b.y != 0.f) { atomic_min_i(P.ext + 2, i); atomic_max_i(P.ext + 3, i); }
-        if (c.x != 0.f || c.y != 0.f) { atomic_min_i(P.ext + 4, i); atomic_max_i(P.ext + 5, i); }
-        if (d.x != 0.f || d.y != 0.f) { atomic_min_i(P.ext + 6, i); atomic_max_i(P.ext + 7, i); }
+    for (int k = 0; k < P.lines; ++k) {
+        if (P.r0 + k > P.r1 - k && k > 0) break;
+        int* e = P.ext + 8 * k;
+        const int ra = P.r0 + k, rb = P.r1 - k, ca = P.c0 + k, cb = P.c1 - k;
+        if (rb < 0 || cb < 0 || ra >= P.pn || ca >= P.pn) break;
+        for (int i = ctx.tid(); i < P.pn; i += ctx.bdim()) {
+            const cplx a = P.pupil[(size_t)ra * P.pn + i], b = P.pupil[(size_t)rb * P.pn + i];
+            const cplx c = P.pupil[(size_t)i * P.pn + ca], d = P.pupil[(size_t)i * P.pn + cb];
+            if (a.x != 0.f || a.y != 0.f) { atomic_min_i(e + 0, i); atomic_max_i(e + 1, i); }
+            if (b.x != 0.f || b.y != 0.f) { atomic_min_i(e + 2, i); atomic_max_i(e + 3, i); }
+            if (c.x != 0.f || c.y != 0.f) { atomic_min_i(e + 4, i); atomic_max_i(e + 5, i); }
+            if (d.x != 0.f || d.y != 0.f) { atomic_min_i(e + 6, i); atomic_max_i(e + 7, i); }
+        }
     }
 }
 
@@ -182,9 +188,9 @@ __global__ void coarse_unperm_kernel(const __grid_constant__ CoarseUnpermParams 
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < 2 * P.M) coarse_unperm_elem(P, blockIdx.y, b);
 }
-__global__ void assemble_kernel(const __grid_constant__ AssembleParams P) {
+__global__ void assemble_kernel(const __grid_constant__ AssembleParams P, int cols) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j <= P.Nc) assemble_elem(P, blockIdx.y, j);
+    if (j < cols) assemble_elem(P, blockIdx.y, j);
 }
 __global__ void finalize_kernel(const __grid_constant__ FinalizeParams P) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -336,8 +342,8 @@ struct litho_plan {
     // fast path (fast_kernels.h): coarse grid Nc = 2*Mf, q = N/Nc
     int path;        // 1 = generic fine grid, 2 = fast coarse grid
     int Mf, Nc, q, ppt;
-    int rim_row, rim_col;  // Sr == Mf+1 / Sc == Mf+1: the +-Mf frequency line needs the rim sums
-    int ext[8];      // non-zero extents of the first/last window row and column (window coordinates)
+    int er, ec;      // Sr-1-Mf / Sc-1-Mf: frequency lines Mf .. Mf+er (ec) need the rim sums; -1: none
+    int ext[4][RIM_LINES][2];  // non-zero extents of the outermost window rows/columns (RimParams::ext)
     cplx* tables;    // device twiddle tables of the fast kernels (owned by the plan)
     int n_sm;
     int tma_cols;    // > 0: columns per tile of the TMA-staged column kernel (0: plain global loads)
@@ -519,21 +525,26 @@ int litho_pupil_bbox(const void* pupil, int pn, int* bbox_host, void* stream) {
 }
 
 int litho_pupil_support(const void* pupil, int pn, int* support_host, void* stream) {
-    if (!support_host) return fail(LITHO_ERR_ARG, "pupil_support: null argument");
+    return litho_pupil_support_lines(pupil, pn, 1, support_host, stream);
+}
+
+int litho_pupil_support_lines(const void* pupil, int pn, int lines, int* support_host, void* stream) {
+    if (!support_host || lines < 1 || lines > RIM_LINES) return fail(LITHO_ERR_ARG, "pupil_support: bad argument");
     int rc = litho_pupil_bbox(pupil, pn, support_host, stream);
     if (rc) return rc;
     const int r0 = support_host[0], r1 = support_host[1], c0 = support_host[2], c1 = support_host[3];
+    const int n = 8 * lines;
+    for (int i = 0; i < n; ++i) support_host[4 + i] = (i & 1) ? -1 : pn;   // empty extents: lo = pn, hi = -1
     if (r1 < r0) {
-        for (int i = 4; i < 12; ++i) support_host[i] = (i & 1) ? -1 : 0;
+        for (int i = 0; i < n; ++i) support_host[4 + i] = (i & 1) ? -1 : 0;
         return LITHO_OK;
     }
     litho_stream_t st = (litho_stream_t)stream;
     int* dext = nullptr;
-    BE_CHECK(be_malloc((void**)&dext, 8 * sizeof(int)));
-    int init[8] = {pn, -1, pn, -1, pn, -1, pn, -1};
-    rc = be_h2d(dext, init, sizeof(init), st);
+    BE_CHECK(be_malloc((void**)&dext, n * sizeof(int)));
+    rc = be_h2d(dext, support_host + 4, n * sizeof(int), st);
     if (rc == 0) {
-        ExtParams P{(const cplx*)pupil, pn, r0, r1, c0, c1, dext};
+        ExtParams P{(const cplx*)pupil, pn, r0, r1, c0, c1, lines, dext};
 #if defined(LITHO_EMU)
         litho_emu::launch(1, 1, 1, 32, 0, [&](const litho_emu::EmuCtx& c, char*) { ext_body(P, c); });
 #else
@@ -541,7 +552,7 @@ int litho_pupil_support(const void* pupil, int pn, int* support_host, void* stre
         rc = (int)cudaGetLastError();
 #endif
     }
-    if (rc == 0) rc = be_d2h_sync(support_host + 4, dext, 8 * sizeof(int), st);
+    if (rc == 0) rc = be_d2h_sync(support_host + 4, dext, n * sizeof(int), st);
     be_free(dext);
     if (rc != 0) return fail(LITHO_ERR_CUDA, std::string("pupil_support: ") + be_errstr(rc));
     return LITHO_OK;
@@ -574,16 +585,19 @@ int litho_shift_bounds(const int32_t* shifts, int n_src, int* bounds_host, void*
 
 int litho_plan_create(int pn, int N, const int* bbox, int flags, litho_plan_t** out) {
     if (!bbox) return fail(LITHO_ERR_ARG, "plan_create: null argument");
-    // without measured extents the rim lines are assumed to span the whole window (correct, just slower)
-    int sup[12];
-    for (int i = 0; i < 4; ++i) sup[i] = bbox[i];
-    sup[4] = sup[6] = bbox[2]; sup[5] = sup[7] = bbox[3];   // first/last row: columns c0..c1
-    sup[8] = sup[10] = bbox[0]; sup[9] = sup[11] = bbox[1]; // first/last column: rows r0..r1
-    return litho_plan_create_ex(pn, N, sup, flags, out);
+    return litho_plan_create_lines(pn, N, bbox, 0, flags, out);
 }
 
-int litho_plan_create_ex(int pn, int N, const int* bbox, int flags, litho_plan_t** out) {
+int litho_plan_create_ex(int pn, int N, const int* support, int flags, litho_plan_t** out) {
+    return litho_plan_create_lines(pn, N, support, 1, flags, out);
+}
+
+// support = bbox (4 ints) followed by the extents of `lines` outermost rows/columns (8 ints per line, the layout
+// litho_pupil_support_lines returns).  Lines without measured extents are assumed to span the whole window
+// (correct, just slower).
+int litho_plan_create_lines(int pn, int N, const int* bbox, int lines, int flags, litho_plan_t** out) {
     if (!out || !bbox) return fail(LITHO_ERR_ARG, "plan_create: null argument");
+    if (lines < 0 || lines > RIM_LINES) return fail(LITHO_ERR_ARG, "plan_create: lines out of range");
     if (pn < 2 || (pn & 1)) return fail(LITHO_ERR_ARG, "plan_create: pixelNumber must be even and >= 2 (odd grids make the reference transform length N-1)");
     if (!is_pow2(N) || N > 16384 || N < 16) return fail(LITHO_ERR_ARG, "plan_create: N must be a power of two in [16,16384]");
     if (N < pn) return fail(LITHO_ERR_ARG, "plan_create: N < pixelNumber is unsupported (the reference raises, SURVEY Q7)");
@@ -616,7 +630,7 @@ int litho_plan_create_ex(int pn, int N, const int* bbox, int flags, litho_plan_t
     }
     size_t per = (size_t)p->zp.R * p->Sr * p->zp.Wr * sizeof(cplx);
     // ---- fast path eligibility: even window fit S <= Mf+1, coarse grid Nc = 2*Mf no finer than N ----
-    p->path = 1; p->tables = nullptr; p->tables_c = nullptr; p->tma_box_rows = 0; p->Mf = p->Nc = p->q = 0; p->rim_row = p->rim_col = 0;
+    p->path = 1; p->tables = nullptr; p->tables_c = nullptr; p->tma_box_rows = 0; p->Mf = p->Nc = p->q = 0; p->er = p->ec = -1;
     p->fused = 0; p->fused_B = 2; p->counters = nullptr; p->counters_cap = 0; p->tma_cols = 0;
     p->last_ws = nullptr; p->last_batch = 0;
     for (int i = 0; i < LITHO_TSLOTS; ++i) p->cols_recorded[i] = 0;
@@ -632,8 +646,10 @@ int litho_plan_create_ex(int pn, int N, const int* bbox, int flags, litho_plan_t
             p->n_sm = n;
     }
 #endif
+    // fast path: window fits S <= Mf + 1 + RIM_EXTRA (the inputs beyond Mf fold onto the first slots and the
+    // frequency lines they add are carried by the rim sums)
     int Mf = 32;
-    while (Mf < S - 1) Mf <<= 1;
+    while (Mf + RIM_EXTRA < S - 1) Mf <<= 1;
     if (!(flags & LITHO_PLAN_GENERIC) && Mf <= 4096 && 2 * Mf <= N) {
         // points per thread of the fast FFTs: 32 (one exchange, 128 regs) or 16 (two exchanges, 64 regs,
         // twice the resident warps); LITHO_FAST_PPT overrides the per-size default for experiments
@@ -727,15 +743,23 @@ int litho_plan_create_ex(int pn, int N, const int* bbox, int flags, litho_plan_t
                 return fail(LITHO_ERR_CUDA, std::string("plan_create: compact tables: ") + be_errstr(rc));
             }
         }
-        p->rim_row = (p->Sr == Mf + 1);
-        p->rim_col = (p->Sc == Mf + 1);
-        // extents in window coordinates, clamped to the window
-        const int* e = bbox + 4;
+        p->er = p->Sr > Mf ? p->Sr - 1 - Mf : -1;
+        p->ec = p->Sc > Mf ? p->Sc - 1 - Mf : -1;
+        // extents in window coordinates, clamped to the window; full width where none were measured
         auto clampi = [](int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); };
-        p->ext[0] = clampi(e[0] - c0, 0, p->Sc - 1); p->ext[1] = clampi(e[1] - c0, 0, p->Sc - 1);  // first row
-        p->ext[2] = clampi(e[2] - c0, 0, p->Sc - 1); p->ext[3] = clampi(e[3] - c0, 0, p->Sc - 1);  // last row
-        p->ext[4] = clampi(e[4] - r0, 0, p->Sr - 1); p->ext[5] = clampi(e[5] - r0, 0, p->Sr - 1);  // first column
-        p->ext[6] = clampi(e[6] - r0, 0, p->Sr - 1); p->ext[7] = clampi(e[7] - r0, 0, p->Sr - 1);  // last column
+        for (int k = 0; k < RIM_LINES; ++k) {
+            for (int side = 0; side < 4; ++side) {
+                const int len = side < 2 ? p->Sc : p->Sr, org = side < 2 ? c0 : r0;
+                int lo = 0, hi = len - 1;
+                if (k < lines) {
+                    lo = bbox[4 + 8 * k + 2 * side] - org;
+                    hi = bbox[4 + 8 * k + 2 * side + 1] - org;
+                    if (hi >= lo) { lo = clampi(lo, 0, len - 1); hi = clampi(hi, 0, len - 1); }
+                    else { lo = 0; hi = -1; }   // an empty line (possible for k > 0)
+                }
+                p->ext[side][k][0] = lo; p->ext[side][k][1] = hi;
+            }
+        }
         per = (size_t)2 * p->Sr * Mf * sizeof(cplx);
     }
     // batch (source points per launch pair).  Generic path: T of one batch around 64 MB.  Fast path:
@@ -769,16 +793,17 @@ void litho_plan_destroy(litho_plan_t* p) {
     delete p;  // the w_L twiddle table belongs to the process-wide cache
 }
 
+// coarse plane [2][2][Mf][Mf], then the rim sums: RIM_LINES row lines of 2*Sc-1 complex, RIM_LINES column lines
+// of 2*Sr-1 complex (RimParams::frow / fcol)
+static uint64_t rim_row_floats(const litho_plan* p) { return (uint64_t)2 * RIM_LINES * (2 * p->Sc - 1); }
+static uint64_t rim_col_floats(const litho_plan* p) { return (uint64_t)2 * RIM_LINES * (2 * p->Sr - 1); }
 static uint64_t intensity_elems(const litho_plan* p) {
-    if (p->path == 2)  // coarse plane [2][2][Mf][Mf] + the two rim lines (2*Mf+1 complex each)
-        return (uint64_t)4 * p->Mf * p->Mf + (uint64_t)4 * (2 * p->Mf + 1);
+    if (p->path == 2) return (uint64_t)4 * p->Mf * p->Mf + rim_row_floats(p) + rim_col_floats(p);
     return (uint64_t)p->zp.R * p->zp.R * p->zp.Wr * p->zp.Wr;
 }
 
 static float* rim_row_ptr(const litho_plan* p, float* intensity) { return intensity + (size_t)4 * p->Mf * p->Mf; }
-static float* rim_col_ptr(const litho_plan* p, float* intensity) {
-    return intensity + (size_t)4 * p->Mf * p->Mf + (size_t)2 * (2 * p->Mf + 1);
-}
+static float* rim_col_ptr(const litho_plan* p, float* intensity) { return rim_row_ptr(p, intensity) + rim_row_floats(p); }
 
 int litho_plan_get_info(const litho_plan_t* p, litho_plan_info_t* info) {
     if (!p || !info) return fail(LITHO_ERR_ARG, "plan_get_info: null argument");
@@ -829,6 +854,7 @@ struct FinalizeLayout {
     ZoomPlan z1, z2;
     AxisOut o1, o2;
     int fpc1, cb1, fpc2, cb2;
+    int spec_rows, spec_cols;
 };
 
 static int finalize_layout(const litho_plan* p, FinalizeLayout* L) {
@@ -840,16 +866,20 @@ static int finalize_layout(const litho_plan* p, FinalizeLayout* L) {
         // step 1: centred forward DFT of the Nc x Nc coarse plane (one length-Nc FFT per line)
         L->z1.L = Nc; L->z1.M = Nc; L->z1.R = 1; L->z1.Wr = Nc;
         L->o1.W = Nc; L->o1.center = Nc / 2;
-        // step 2: inverse zoom of the (Nc+1)^2 spectrum to the pn centre pixels of the N grid
-        L->z2.L = N; L->z2.M = Nc; L->z2.R = N / Nc; L->z2.Wr = (pn + L->z2.R - 1) / L->z2.R;
+        // step 2: inverse zoom of the (Nc+1+2Er) x (Nc+1+2Ec) spectrum to the pn centre pixels of the N grid;
+        // a spectrum wider than Nc+1 needs the next sub-FFT length (2*Nc <= N because q > 1)
+        const int Er = p->er > 0 ? p->er : 0, Ec = p->ec > 0 ? p->ec : 0;
+        const int M2 = (Er > 0 || Ec > 0) ? 2 * Nc : Nc;
+        L->spec_rows = Nc + 1 + 2 * Er; L->spec_cols = Nc + 1 + 2 * Ec;
+        L->z2.L = N; L->z2.M = M2; L->z2.R = N / M2; L->z2.Wr = (pn + L->z2.R - 1) / L->z2.R;
         L->o2.W = pn; L->o2.center = pn / 2;
         if (dispatch_shape(Nc, &L->fpc1, &L->cb1)) return 1;
-        L->fpc2 = L->fpc1; L->cb2 = L->cb1;
+        if (dispatch_shape(M2, &L->fpc2, &L->cb2)) return 1;
         L->a_off = off;    off += align16((size_t)Nc * Nc * sizeof(float));
         L->t1_off = off;   off += align16((size_t)Nc * Nc * sizeof(cplx));
         L->fhat_off = off; off += align16((size_t)Nc * Nc * sizeof(cplx));
-        L->spec_off = off; off += align16((size_t)(Nc + 1) * (Nc + 1) * sizeof(cplx));
-        L->t2_off = off;   off += align16((size_t)L->z2.R * (Nc + 1) * L->z2.Wr * sizeof(cplx));
+        L->spec_off = off; off += align16((size_t)L->spec_rows * L->spec_cols * sizeof(cplx));
+        L->t2_off = off;   off += align16((size_t)L->z2.R * L->spec_rows * L->z2.Wr * sizeof(cplx));
     }
     L->fine_off = off;
     off += align16((size_t)pn * pn * sizeof(float));
@@ -967,7 +997,7 @@ int litho_abbe_fft_accumulate_ex(const litho_plan_t* p, const void* maskFT, cons
                               p->tma_cols) == 0) {
                 fc.use_tma = p->tma_cols;
                 fc.nbox = nbox;
-                fc.rim = p->Sr > p->Mf;
+                fc.rim = p->Sr > p->Mf ? p->Sr - p->Mf : 0;
                 fc.tables_c = p->tables_c;
             }
         }
@@ -1012,18 +1042,28 @@ int litho_abbe_fft_accumulate_ex(const litho_plan_t* p, const void* maskFT, cons
             if (phases & 2) BE_CHECK(dispatch_fast_cols(p->Mf, p->ppt, fc, st));
         }
         }
-        if ((phases & 2) && p->q > 1 && (p->rim_row || p->rim_col)) {
+        if ((phases & 2) && p->q > 1 && (p->er >= 0 || p->ec >= 0)) {
             RimParams rm;
             memset(&rm, 0, sizeof(rm));
             rm.pupil = (const cplx*)pupil; rm.mask = (const cplx*)maskFT; rm.pn = p->pn;
             rm.pr0 = p->bbox[0]; rm.pc0 = p->bbox[2]; rm.Sr = p->Sr; rm.Sc = p->Sc; rm.M = p->Mf;
             rm.shifts = (const int2_*)shifts; rm.weights = weights; rm.n_src = n_src;
             memcpy(rm.ext, p->ext, sizeof(rm.ext));
-            rm.do_row = p->rim_row; rm.do_col = p->rim_col;
+            rm.er = p->er; rm.ec = p->ec;
             rm.frow = rim_row_ptr(p, intensity); rm.fcol = rim_col_ptr(p, intensity);
-            const int n_row = (p->ext[3] - p->ext[2] + 1) + (p->ext[1] - p->ext[0] + 1);
-            const int n_col = (p->ext[7] - p->ext[6] + 1) + (p->ext[5] - p->ext[4] + 1);
-            const size_t smem = (size_t)(n_row > n_col ? n_row : n_col) * sizeof(cplx);
+            // shared memory: the longest (lo, hi) pair of lines that gets correlated
+            int longest = 1;
+            for (int axis = 0; axis < 2; ++axis) {
+                const int e = axis == 0 ? p->er : p->ec;
+                for (int k = 0; k <= e; ++k)
+                    for (int t = 0; t + k <= e; ++t) {
+                        const int b = e - k - t;
+                        const int nl = p->ext[axis * 2][t][1] - p->ext[axis * 2][t][0] + 1;
+                        const int nh = p->ext[axis * 2 + 1][b][1] - p->ext[axis * 2 + 1][b][0] + 1;
+                        if (nl > 0 && nh > 0 && nl + nh > longest) longest = nl + nh;
+                    }
+            }
+            const size_t smem = (size_t)longest * sizeof(cplx);
 #if defined(LITHO_EMU)
             litho_emu::launch(n_src, 1, 1, 64, smem, [&](const litho_emu::EmuCtx& c, char* s) { rim_body(rm, c, (cplx*)s); });
 #else
@@ -1125,25 +1165,27 @@ static int fine_plane_fast(const litho_plan* p, const float* intensity, void* wo
     AssembleParams as;
     as.fhat = fhat; as.frow = rim_row_ptr(p, const_cast<float*>(intensity));
     as.fcol = rim_col_ptr(p, const_cast<float*>(intensity));
-    as.Nc = Nc; as.do_row = p->rim_row; as.do_col = p->rim_col; as.out = spec;
+    as.Nc = Nc; as.er = p->er; as.ec = p->ec; as.Sr = p->Sr; as.Sc = p->Sc; as.out = spec;
+    const int SR = L.spec_rows, SC = L.spec_cols;
 #if defined(LITHO_EMU)
-    for (int i = 0; i <= Nc; ++i)
-        for (int j = 0; j <= Nc; ++j) assemble_elem(as, i, j);
+    for (int i = 0; i < SR; ++i)
+        for (int j = 0; j < SC; ++j) assemble_elem(as, i, j);
 #else
-    assemble_kernel<<<dim3((Nc + 1 + 255) / 256, Nc + 1, 1), 256, 0, st>>>(as);
+    assemble_kernel<<<dim3((SC + 255) / 256, SR, 1), 256, 0, st>>>(as, SC);
     BE_CHECK((int)cudaGetLastError());
 #endif
-    {   // step 4: fine[i][j] = Re sum_{m,n=-K..K} spec[m][n] exp(+2 pi i (m i' + n j')/N), i' = i - pn/2
-        AxisIn ax; ax.first = 0; ax.period = BIG; ax.center = Nc / 2; ax.S = Nc + 1;
-        const int R = L.z2.R;
+    {   // step 4: fine[i][j] = Re sum_{m,n} spec[m][n] exp(+2 pi i (m i' + n j')/N), i' = i - pn/2
+        AxisIn axc; axc.first = 0; axc.period = BIG; axc.center = (SC - 1) / 2; axc.S = SC;   // along a spectrum row
+        AxisIn axr; axr.first = 0; axr.period = BIG; axr.center = (SR - 1) / 2; axr.S = SR;   // along a spectrum column
+        const int R = L.z2.R, M2 = L.z2.M;
         RowsParams rp; memset(&rp, 0, sizeof(rp));
-        rp.cplx_in = spec; rp.in_pitch = Nc + 1; rp.lines = Nc + 1; rp.ax = ax; rp.out = L.o2; rp.plan = L.z2;
+        rp.cplx_in = spec; rp.in_pitch = SC; rp.lines = SR; rp.ax = axc; rp.out = L.o2; rp.plan = L.z2;
         rp.twL = tw2; rp.T = T2;
         ColsParams cp; memset(&cp, 0, sizeof(cp));
-        cp.T = T2; cp.batch = 1; cp.Rc = R; cp.Wrc = L.z2.Wr; cp.outc = L.o2; cp.ax = ax; cp.out = L.o2; cp.plan = L.z2;
+        cp.T = T2; cp.batch = 1; cp.Rc = R; cp.Wrc = L.z2.Wr; cp.outc = L.o2; cp.ax = axr; cp.out = L.o2; cp.plan = L.z2;
         cp.twL = tw2; cp.real_out = fine; cp.field_pitch = pn; cp.conj_out = 0; cp.scale = 1.f;
-        BE_CHECK(dispatch_rows(Nc, ROW_CPLX_PLANE, rp, ((Nc + 1) * R + L.fpc2 - 1) / L.fpc2, 1, st));
-        BE_CHECK(dispatch_cols(Nc, EPI_FIELD, cp, R * ((L.z2.Wr + L.cb2 - 1) / L.cb2), R, st));
+        BE_CHECK(dispatch_rows(M2, ROW_CPLX_PLANE, rp, (SR * R + L.fpc2 - 1) / L.fpc2, 1, st));
+        BE_CHECK(dispatch_cols(M2, EPI_FIELD, cp, R * ((L.z2.Wr + L.cb2 - 1) / L.cb2), R, st));
     }
     memset(view, 0, sizeof(*view));
     view->mode = 1; view->iperm = fine; view->pitch = pn;

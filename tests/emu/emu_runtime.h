@@ -94,7 +94,7 @@ struct EmuCtx {
     // like the hardware's out-of-bounds fill).  The mbarrier word counts completed phases; a waiter yields
     // until the phase of its parity has completed, as the hardware's try_wait.parity loop does.
     void mbar_init(unsigned long long* bar, int) const { *bar = 0; }
-    void tile_load(void* dst, const litho::TileMap& tm, int row, int col, int nbox, int rim_elem,
+    void tile_load(void* dst, const litho::TileMap& tm, int row, int col, int nbox, int rim_rows, int rim_elem,
                    unsigned long long* bar) const {
         char* d = (char*)dst;
         for (int i = 0; i < nbox; ++i)
@@ -103,9 +103,9 @@ struct EmuCtx {
                 if (y < tm.rows) memcpy(d, tm.base + y * tm.pitch + col, (size_t)tm.box_cols * 8);
                 else memset(d, 0, (size_t)tm.box_cols * 8);
             }
-        if (rim_elem >= 0)
-            memcpy((char*)dst + (size_t)rim_elem * 8, tm.base + (long long)(row + nbox * tm.box_rows) * tm.pitch + col,
-                   (size_t)tm.box_cols * 8);
+        for (int k = 0; k < rim_rows; ++k)
+            memcpy((char*)dst + (size_t)(rim_elem + k * tm.box_cols) * 8,
+                   tm.base + (long long)(row + nbox * tm.box_rows + k) * tm.pitch + col, (size_t)tm.box_cols * 8);
         ++*bar;
         ++cur_sched()->progress;
     }

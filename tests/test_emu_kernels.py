@@ -63,6 +63,39 @@ def test_emu_fast_path_dense_window(pn, ps, win):
     assert O.rel_l2(fast, gen) < H.TOL
 
 
+@pytest.mark.parametrize("wr,wc", [(34, 34), (35, 35), (35, 33), (31, 34), (33, 35)])
+@pytest.mark.parametrize("tma", ["1", "0"])
+def test_emu_fast_path_window_beyond_even_fit(monkeypatch, wr, wc, tma):
+    """Windows of M+2 / M+3 samples (M = 32), as the reference's fp16 pupil grid produces at pn = 8192 (support
+    pn/2+3): the inputs beyond M fold onto the first slots and the frequency lines M .. S-1, which alias on the
+    coarse grid, come from the generalised rim sums (row/column pairs, aliased partners subtracted from the interior
+    bins).  Dense random windows make every one of those lines carry energy; rows and columns may differ."""
+    monkeypatch.setenv("LITHO_TMA", tma)
+    pn = 128
+    rng = np.random.default_rng(1000 + 10 * wr + wc)
+    r0, c0 = pn // 2 - wr // 2, pn // 2 - wc // 2
+    pup = np.zeros((pn, pn), np.complex64)
+    pup[r0:r0 + wr, c0:c0 + wc] = rng.standard_normal((wr, wc)) + 1j * rng.standard_normal((wr, wc))
+    mft = (rng.standard_normal((pn, pn)) + 1j * rng.standard_normal((pn, pn))).astype(np.complex64)
+    shifts = np.array([[0, 0], [5, -7], [-r0, pn - (c0 + wc)], [3, 3], [-9, 4]], np.int32)
+    w = np.array([1.0, 2.0, 0.5, 1.5, 0.75], np.float32)
+    fast, info = H.emu_abbe_fft(mft, pup, None, 25.0, 193.0, shifts=shifts, weights=w, postprocess=False, batch=2)
+    assert info["path"] == 2 and info["M"] == 32, info
+    ref = np.zeros((pn, pn))
+    for (d0, d1), wi in zip(shifts, w):
+        ref += wi * np.abs(O.calculate_fft_aerial(np.roll(pup, (d0, d1), (0, 1)), mft, pn, 256)) ** 2
+    assert O.rel_l2(fast, ref) < H.TOL
+    # sparse rim lines (only a short stretch populated, like a disc's edge) with measured extents
+    pup2 = pup.copy()
+    pup2[r0, :] = 0; pup2[r0, c0 + 10:c0 + 15] = 1 + 1j
+    pup2[r0 + wr - 1, :] = 0; pup2[r0 + wr - 1, c0 + 20:c0 + 22] = 2 - 1j
+    pup2[:, c0] = 0; pup2[r0 + 5:r0 + 9, c0] = -1j
+    fast2, info2 = H.emu_abbe_fft(mft, pup2, None, 25.0, 193.0, shifts=shifts, postprocess=True, batch=3)
+    assert info2["path"] == 2
+    ref2 = O.abbe_image(mft, pup2, None, 25, 4 / pn, 193.0, True, np.complex128, shifts=shifts)
+    assert O.rel_l2(fast2, ref2) < H.TOL
+
+
 @pytest.mark.parametrize("tma", ["1", "0"])
 def test_emu_column_pass_tma_and_plain_agree(monkeypatch, tma):
     """The TMA-staged column kernel (tile of source point sl+1 copied to shared memory while sl is transformed)

@@ -424,37 +424,43 @@ def test_cfg4_size_single_points_against_oracle(L, dev):
     assert np.linalg.norm(mine - mft) / np.linalg.norm(mft) < H.TOL
 
 
-def test_cfg5_size_fast_equals_generic(L, dev):
+@pytest.mark.parametrize("trim", [False, True])
+def test_cfg5_size_fast_equals_generic(L, dev, trim):
     """BASELINE cfg5 grid (8192 px, N = 16384, sub-FFT 4096 = radix 32x32x4): fast coarse-grid path against the
-    generic fine-grid kernels on one source point (the oracle would need a 4 GB complex128 FFT here)."""
+    generic fine-grid kernels on one source point (the oracle would need a 4 GB complex128 FFT here).
+    trim=False: the reference's own pupil, whose support is 4099 = M+3 px wide -- the fast path folds the two
+    extra rows/columns and takes the frequency lines M..M+2 from the generalised rim sums; trim=True: the even
+    fit M+1."""
     from lithographysimulator_b200.imaging import AbbeEngine
     pn = 8192
     ab = torch.tensor([0, 0, 0.01, 0, -150, 0.01], dtype=torch.float16, device=dev)
     pf = L.Pupil(pn, 193.0, 0.7, ab, dev).generatePupilFunction()
     eng = AbbeEngine.get(dev)
     # At 8192 px the reference's fp16 grid collapses neighbouring coordinates near |x| = 1, so its pupil
-    # support is 4099 px wide (one more than 2*pn/4+1 on each side): that pupil takes the generic kernels.
+    # support is 4099 px wide (one more than 2*pn/4+1 on each side).
     assert eng.pupil_support(pf)[:4] == (2047, 6145, 2047, 6145)
-    # Trim it to the 4097-px window that the sub-FFT-4096 fast kernels cover.
-    pf[:2048] = 0
-    pf[6145:] = 0
-    pf[:, :2048] = 0
-    pf[:, 6145:] = 0
+    if trim:
+        pf[:2048] = 0
+        pf[6145:] = 0
+        pf[:, :2048] = 0
+        pf[:, 6145:] = 0
     g = torch.Generator(device="cpu").manual_seed(3)
     mft = torch.complex(torch.randn((pn, pn), generator=g), torch.randn((pn, pn), generator=g)).to(dev)
     sh = torch.tensor([[1500, -900]], dtype=torch.int32)
     kw = dict(pixelSize=25, deltaK=4 / pn, wavelength=193.0, shifts=sh, postprocess=False)
     fast = eng.abbe_fft(mft, pf, None, **kw)
     gen = eng.abbe_fft(mft, pf, None, generic=True, **kw)
-    assert eng.plan_for(pn, 2 * pn, eng.pupil_support(pf), sh.to(dev)).path == 2
+    plan = eng.plan_for(pn, 2 * pn, eng.pupil_support(pf), sh.to(dev))
+    assert plan.path == 2 and plan.M == 4096
     num = torch.linalg.vector_norm((fast - gen).double())
     den = torch.linalg.vector_norm(gen.double())
     assert float(num / den) < H.TOL
 
 
 def test_cfg5_reference_pupil_against_oracle(L, dev):
-    """BASELINE cfg5 grid with the reference's own 8192-px pupil (support 4099 px, generic fine-grid kernels,
-    N = 16384): one source point against the oracle's FFT solver (complex64 here: a 16384^2 complex128 plane
+    """BASELINE cfg5 grid with the reference's own 8192-px pupil (support 4099 px = sub-FFT 4096 + 3: fast path
+    with folded extra rows/columns and three rim lines per side, N = 16384): one source point against the
+    oracle's FFT solver (complex64 here: a 16384^2 complex128 plane
     would need 4 GB per copy; the oracle's c64/c128 gap is 1e-7)."""
     from lithographysimulator_b200.imaging import AbbeEngine
     pn = 8192
