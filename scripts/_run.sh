@@ -1,3 +1,5 @@
 mkdir -p gpurun_out
-T="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1"
-$T --master-port 29511 bench.py --gpus 8 --steps 5 --warmup 3 > gpurun_out/r02k_n8_k5.log 2>&1; tail -1 gpurun_out/r02k_n8_k5.log | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('cfg3 n8 k5', d['value'], d['ms_per_step'], d['e2e']['value'])"
+python bench.py > gpurun_out/r02l_bench_default.log 2>&1; tail -1 gpurun_out/r02l_bench_default.log | cut -c1-200
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 300 --csv --log-file gpurun_out/r02l_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/r02l_ncu_launch.log 2>&1
+timeout 400 ncu --set full --cache-control none --clock-control none --import-source on -k regex:abbe_fast -s 12 -c 4 -o gpurun_out/r02l_prof python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/r02l_prof.log 2>&1
+ls -la gpurun_out | grep r02l
