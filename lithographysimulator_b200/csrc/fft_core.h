@@ -80,8 +80,16 @@ LITHO_HD void fft_pass(cplx (&v)[PPT], cplx* sm, int es, int g, const Tw& tw, co
     if constexpr (PASS > 0) {
         // gather this pass's inputs: element g + TG*e -> register e
         sync.sync();
+        if constexpr (TG % PPT == 0) {
+            // padp(g + TG*e) = (g + g/PPT) + e*(TG + TG/PPT) exactly when PPT divides TG: one per-thread base and
+            // compile-time offsets (left to itself the compiler rebuilds the padding with a mask per element)
+            const cplx* gp = sm + (g + g / PPT) * es;
 #pragma unroll
-        for (int e = 0; e < PPT; ++e) v[e] = sm[padp<PPT>(g + TG * e) * es];
+            for (int e = 0; e < PPT; ++e) v[e] = gp[e * (TG + TG / PPT) * es];
+        } else {
+#pragma unroll
+            for (int e = 0; e < PPT; ++e) v[e] = sm[padp<PPT>(g + TG * e) * es];
+        }
         if constexpr (LAST) hook.after_last_gather();
         // twiddle: butterfly b has index j = g + b*TG, k = j mod NS, angle 2*pi*t*k/(NS*R)
 #pragma unroll
@@ -121,6 +129,7 @@ LITHO_HD void fft_pass(cplx (&v)[PPT], cplx* sm, int es, int g, const Tw& tw, co
 template <int M, int PPT, bool FWD, class Tw, class Sync, class Hook = NoHook>
 LITHO_HD void fft_run(cplx (&v)[PPT], cplx* sm, int es, int g, const Tw& tw, const Sync& sync,
                       const Hook& hook = Hook()) {
+    LITHO_ASSUME(((unsigned)g < (unsigned)FftShape<M, PPT>::TG));
     fft_pass<M, PPT, 0, FWD>(v, sm, es, g, tw, sync, hook);
 }
 

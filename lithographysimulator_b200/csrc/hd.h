@@ -17,6 +17,16 @@
 #define LITHO_HD inline
 #define LITHO_D inline
 #endif
+// Value-range hint for the device compiler (index arithmetic such as (g + TG*e)/PPT folds to constants once
+// it knows g < TG); checked for real in the CPU emulation.
+#if defined(__CUDA_ARCH__)
+#define LITHO_ASSUME(x) __builtin_assume(x)
+#elif defined(LITHO_EMU)
+#include <assert.h>
+#define LITHO_ASSUME(x) assert(x)
+#else
+#define LITHO_ASSUME(x) ((void)0)
+#endif
 
 namespace litho {
 
