@@ -96,6 +96,48 @@ def test_emu_fast_path_window_beyond_even_fit(monkeypatch, wr, wc, tma):
     assert O.rel_l2(fast2, ref2) < H.TOL
 
 
+@pytest.mark.parametrize("seed", range(14))
+def test_emu_random_windows_sources_and_grids(seed):
+    """Seeded sweep over the plan space: grid 64/96/128 px, pixel size 12/25/50 nm (N = 4pn, 2pn, pn), pupil
+    windows of any size and position (1 px up to beyond M+3, off-centre), sources inside and outside the no-wrap
+    range (the latter must fall back to the generic kernels), with and without weights and post-processing --
+    each against the oracle's literal restatement of the reference loop."""
+    rng = np.random.default_rng(4242 + seed)
+    pn = int(rng.choice([64, 96, 128]))
+    ps = float(rng.choice([12, 25, 50]))
+    _, N = O.calculate_epsilon_n(4 / pn, ps, 193.0)
+    if N < pn:          # 96 px at 50 nm: the reference itself raises there (SURVEY Q7)
+        ps = 25.0
+        _, N = O.calculate_epsilon_n(4 / pn, ps, 193.0)
+    wr, wc = (int(rng.integers(1, pn // 2 + 8)) for _ in range(2))
+    r0, c0 = int(rng.integers(0, pn - wr + 1)), int(rng.integers(0, pn - wc + 1))
+    pup = np.zeros((pn, pn), np.complex64)
+    pup[r0:r0 + wr, c0:c0 + wc] = rng.standard_normal((wr, wc)) + 1j * rng.standard_normal((wr, wc))
+    if seed % 3 == 0:   # sparse rim lines, as a disc has
+        pup[r0, c0 + wc // 3:] = 0
+        pup[r0:r0 + wr // 2, c0 + wc - 1] = 0
+    mft = (rng.standard_normal((pn, pn)) + 1j * rng.standard_normal((pn, pn))).astype(np.complex64)
+    n_src = int(rng.integers(1, 6))
+    if seed % 4 == 3:   # anywhere on the grid: some points wrap the window around
+        shifts = rng.integers(-pn // 2, pn // 2, (n_src, 2)).astype(np.int32)
+    else:               # inside the no-wrap range
+        shifts = np.stack([rng.integers(-r0, pn - (r0 + wr) + 1, n_src),
+                           rng.integers(-c0, pn - (c0 + wc) + 1, n_src)], 1).astype(np.int32)
+    w = rng.uniform(0.25, 2.0, n_src).astype(np.float32) if seed % 2 else None
+    post = bool(seed % 5 in (1, 2)) and w is None
+    img, info = H.emu_abbe_fft(mft, pup, None, ps, 193.0, shifts=shifts, weights=w, postprocess=post,
+                               batch=int(rng.integers(0, 4)))
+    ref = np.zeros((pn, pn))
+    for i, (d0, d1) in enumerate(shifts):
+        wi = 1.0 if w is None else float(w[i])
+        ref += wi * np.abs(O.calculate_fft_aerial(np.roll(pup, (int(d0), int(d1)), (0, 1)), mft, pn, N)) ** 2
+    if post:
+        eps, _ = O.calculate_epsilon_n(4 / pn, ps, 193.0)
+        ref = O.fft_postprocess(ref, pn, eps, dtype=np.float64)
+    assert img.shape == ref.shape, (img.shape, ref.shape, info)
+    assert O.rel_l2(img, ref) < H.TOL, info
+
+
 @pytest.mark.parametrize("tma", ["1", "0"])
 def test_emu_column_pass_tma_and_plain_agree(monkeypatch, tma):
     """The TMA-staged column kernel (tile of source point sl+1 copied to shared memory while sl is transformed)
