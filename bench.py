@@ -85,6 +85,9 @@ def algorithmic_flops(pn: int, N: int, n_src: int):
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """SM clock and throttle reasons sampled while the benchmark runs: NVML polled from a thread every 10 ms
+    (a timed region can be shorter than nvidia-smi's 100 ms loop), nvidia-smi as the fallback.  mark() brackets
+    the timed region; stop() reports the samples taken inside it (all samples if none fell inside)."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -93,43 +96,86 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.lines = []
+        self.samples = []      # (t, sm_mhz, max_mhz, set of reason names)
+        self.marks = []
+        self.mode = None
+        self._stop = threading.Event()
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+
+            def poll():
+                while not self._stop.is_set():
+                    try:
+                        sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        r = int(get_reasons(h))
+                        self.samples.append((time.perf_counter(), sm, mx, {n for n, b in bits.items() if r & b}))
+                    except Exception:
+                        pass
+                    self._stop.wait(0.01)
+
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            self.mode = "nvml"
+            return
+        except Exception:
+            self.mode = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            self.mode = "nvidia-smi"
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def mark(self):
+        self.marks.append(time.perf_counter())
 
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
+    def _read(self):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.strip().split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                sm, mx = float(f[1]), float(f[2])
             except ValueError:
                 continue
-            for nm, val in zip(names, f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
+            self.samples.append((time.perf_counter(), sm, mx,
+                                 {nm for nm, val in zip(names, f[5:9]) if val.lower().startswith("active")}))
+
+    def stop(self):
+        if self.mode is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML / nvidia-smi"]}
+        self._stop.set()
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        self.thread.join(timeout=2)
+        inside = self.samples
+        if len(self.marks) >= 2:
+            t0, t1 = self.marks[0], self.marks[1]
+            sel = [x for x in self.samples if t0 <= x[0] <= t1]
+            if sel:
+                inside = sel
+        sm = [x[1] for x in inside]
+        mx = [x[2] for x in inside]
+        reasons = set().union(*[x[3] for x in inside]) if inside else set()
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "samples_total": len(self.samples), "source": self.mode,
+                "window": "timed region" if inside is not self.samples else "whole run",
+                "reasons": sorted(reasons)}
 
 
 # ----------------------------------------------------------------------------- reference arm
@@ -313,6 +359,7 @@ def run_ours(args):
         sampler.start()
     ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark()
     t_wall0 = time.perf_counter()
     ev_a.record()
     for _ in range(args.steps):
@@ -321,6 +368,7 @@ def run_ours(args):
     join()
     ev_b.record()
     barrier()
+    sampler.mark()
     t_wall = time.perf_counter() - t_wall0
     ms = ev_a.elapsed_time(ev_b)
     tms = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -495,7 +543,7 @@ def run_ours(args):
                            "subfft": plan.M, "residues": plan.R,
                            "path": "fast coarse-grid (2 FFTs of length M per line, spectral interpolation once per image)"
                            if plan.path == 2 else "generic fine-grid", "sharding": f"source points interleaved over {world} rank(s), "
-                                                                           "one NCCL all-reduce of the intensity plane"},
+                                                                           "one NCCL sum-reduce of the intensity plane per image"},
                 "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
                 "e2e": {"value": 1.0 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": e2e_steps, "rel_l2_vs_resident_path": e2e_check,
