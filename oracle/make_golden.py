@@ -9,8 +9,12 @@ own, so these outputs of the reference itself are the pari
   tests/golden/cfg1.npz        BASELINE cfg1 (256 px) inputs + full image
   tests/golden/cfg2.npz        BASELINE cfg2 (1024 px): strided image sample + moments
   tests/golden/cfg3.npz        BASELINE cfg3 (2048 px): strided image sample + moments
+  tests/golden/cfg4_subset.npz BASELINE cfg4 grid (4096 px, N = 8192): 8 of its 4104 source points
+  tests/golden/cfg5_subset.npz BASELINE cfg5 grid (8192 px, N = 16384, the reference's own 4099-px-wide pupil at
+                               defocus -150 nm): 3 of its 980 source points
+                               (the full configs would take the reference hours: SURVEY section 8c)
 
-Usage:  python oracle/make_golden.py [kat cfg1 cfg2 cfg3]
+Usage:  python oracle/make_golden.py [kat cfg1 cfg2 cfg3 cfg4_subset cfg5_subset]
 """
 from __future__ import annotations
 
@@ -143,6 +147,38 @@ def make_cfg(name: str, full_image: bool):
     print(name, "written; reference abbeImage", float(d["seconds"]), "s; total", time.time() - t0, "s")
 
 
+def make_cfg_subset(name: str, n_points: int, sample: int):
+    """A few source points of a large config through the unmodified reference (its loop is strictly per source
+    point, imageformation.py:62-67, so a subset of the source is a valid `lightsource` argument)."""
+    cfg = wl.CONFIGS[name]
+    pn = cfg.pn
+    t0 = time.time()
+    L = ref_ls.LightSource(cfg.sigma_in, cfg.sigma_out, pn, cfg.na, 0, 0, CPU)
+    ls = L.generateAnnular() if cfg.source in ("annular", "conventional") else L.generateQuasar(4, -math.pi / 8)
+    ls = (ls * torch.from_numpy(wl.lattice(pn, cfg.stride))).numpy()
+    rows = np.argwhere(ls != 0)
+    pick = rows[np.linspace(0, len(rows) - 1, n_points).round().astype(int)]   # spread over the source, extremes included
+    sub = np.zeros_like(ls)
+    sub[pick[:, 0], pick[:, 1]] = 1
+    ab = list(cfg.aberrations)
+    if cfg.defocus_sweep:
+        ab[4] = cfg.defocus_sweep[0]
+    d = ref_case(cfg.geometry(), cfg.pixel_size, None, ab, True, cfg.wavelength, cfg.na, ls_tensor=sub)
+    img = d["image"]
+    nz = np.argwhere(d["pupil"] != 0)
+    out = dict(eps=d["eps"], N=d["N"], seconds=d["seconds"], n_src_full=np.int64(len(rows)), aberrations=np.array(ab),
+               shape=np.array(img.shape), img_sum=np.float64(img.sum(dtype=np.float64)),
+               img_sumsq=np.float64((img.astype(np.float64) ** 2).sum()), img_max=np.float64(img.max()),
+               sample_stride=np.int64(sample), image_sample=img[::sample, ::sample].copy(),
+               maskFT_abs_sum=np.float64(np.abs(d["maskFT"]).sum(dtype=np.float64)),
+               maskFT_sample=d["maskFT"][::sample, ::sample].copy(),
+               pupil_nnz=np.int64(len(nz)), pupil_bbox=np.array([nz[:, 0].min(), nz[:, 0].max(), nz[:, 1].min(), nz[:, 1].max()]),
+               pupil_sample=d["pupil"][::sample, ::sample].copy(), ls_rows=pick.astype(np.int32))
+    np.savez_compressed(os.path.join(OUT, f"{name}_subset.npz"), **out)
+    print(name, "subset written;", n_points, "points; reference abbeImage", float(d["seconds"]), "s; total",
+          time.time() - t0, "s; image", img.shape, "pupil bbox", out["pupil_bbox"])
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
@@ -150,5 +186,9 @@ if __name__ == "__main__":
     for w in what:
         if w == "kat":
             make_kat()
+        elif w == "cfg4_subset":
+            make_cfg_subset("cfg4", 8, 16)
+        elif w == "cfg5_subset":
+            make_cfg_subset("cfg5", 3, 32)
         else:
             make_cfg(w, full_image=(w == "cfg1"))

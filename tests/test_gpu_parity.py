@@ -477,3 +477,31 @@ def test_cfg5_reference_pupil_against_oracle(L, dev):
     e = O.calculate_fft_aerial(np.roll(pf_ref, (1500, -900), (0, 1)), mft, pn, 2 * pn, np.complex64)
     ref = e.real.astype(np.float64) ** 2 + e.imag.astype(np.float64) ** 2
     assert O.rel_l2(img, ref) < H.TOL
+
+
+@pytest.mark.parametrize("name", ["cfg4", "cfg5"])
+def test_largest_grids_against_reference_subset_golden(L, dev, golden_dir, name):
+    """BASELINE cfg4 (4096 px, N = 8192) and cfg5 (8192 px, N = 16384, the reference's 4099-px-wide pupil) through
+    the whole object chain -- Mask.fraunhofer, Pupil, abbeImage, all on the GPU builders and kernels -- against
+    images the unmodified reference produced for a handful of those configs' source points
+    (tests/golden/cfg{4,5}_subset.npz, oracle/make_golden.py; the full configs take the reference hours)."""
+    z = np.load(f"{golden_dir}/{name}_subset.npz")
+    cfg = wl.CONFIGS[name]
+    pn, st = cfg.pn, int(z["sample_stride"])
+    mask = L.Mask(torch.from_numpy(cfg.geometry()), cfg.pixel_size, dev)
+    mft = mask.fraunhofer(cfg.wavelength, True)
+    ref_m = torch.from_numpy(z["maskFT_sample"]).to(dev)
+    assert float(torch.linalg.vector_norm(mft[::st, ::st] - ref_m) / torch.linalg.vector_norm(ref_m)) < 1e-5
+    ab = torch.tensor(z["aberrations"], dtype=torch.float16, device=dev)
+    pf = L.Pupil(pn, cfg.wavelength, cfg.na, ab, dev).generatePupilFunction()
+    assert int((pf != 0).sum()) == int(z["pupil_nnz"])
+    assert float((pf[::st, ::st] - torch.from_numpy(z["pupil_sample"]).to(dev)).abs().max()) < 1e-3
+    rows = torch.from_numpy(z["ls_rows"].astype(np.int64)).to(dev)
+    ls = torch.zeros((pn, pn), dtype=torch.int64, device=dev)
+    ls[rows[:, 0], rows[:, 1]] = 1
+    img = L.abbeImage(mask, mft, pf, ls, cfg.pixel_size, mask.deltaK, cfg.wavelength, True, dev)
+    assert tuple(img.shape) == tuple(z["shape"])
+    got = img[::st, ::st].cpu().numpy()
+    assert O.rel_l2(got, z["image_sample"]) < H.TOL
+    assert abs(float(img.sum(dtype=torch.float64)) / float(z["img_sum"]) - 1) < 1e-5
+    assert abs(float((img.double() ** 2).sum()) / float(z["img_sumsq"]) - 1) < 2e-5
