@@ -14,7 +14,10 @@ own, so these outputs of the reference itself are the pari
                                defocus -150 nm): 3 of its 980 source points
                                (the full configs would take the reference hours: SURVEY section 8c)
 
-Usage:  python oracle/make_golden.py [kat cfg1 cfg2 cfg3 cfg4_subset cfg5_subset]
+  tests/golden/cfg4.npz, cfg5.npz  the FULL cfg4 (4104 points) and cfg5 (980 points, first focus value) images:
+                               about an hour of CPU each, not part of the default list
+
+Usage:  python oracle/make_golden.py [kat cfg1 cfg2 cfg3 cfg4_subset cfg5_subset cfg4 cfg5]
 """
 from __future__ import annotations
 
@@ -125,21 +128,26 @@ def make_kat():
     print("kat_small written", len(out), "arrays")
 
 
-def make_cfg(name: str, full_image: bool):
+def make_cfg(name: str, full_image: bool, sample: int = SAMPLE):
+    """A whole BASELINE config through the unmodified reference (cfg5: its first focus value, -150 nm)."""
     cfg = wl.CONFIGS[name]
     t0 = time.time()
     kind = cfg.source
+    ab = list(cfg.aberrations)
+    if cfg.defocus_sweep:
+        ab[4] = cfg.defocus_sweep[0]
     d = ref_case(cfg.geometry(), cfg.pixel_size, (kind, cfg.sigma_in, cfg.sigma_out, cfg.stride, 0, 0),
-                 cfg.aberrations, True, cfg.wavelength, cfg.na)
+                 ab, True, cfg.wavelength, cfg.na)
     img = d["image"]
     out = dict(eps=d["eps"], N=d["N"], seconds=d["seconds"], n_src=np.int64((d["lightsource"] != 0).sum()),
+               aberrations=np.array(ab),
                shape=np.array(img.shape), img_sum=np.float64(img.sum(dtype=np.float64)),
                img_sumsq=np.float64((img.astype(np.float64) ** 2).sum()), img_max=np.float64(img.max()),
-               sample_stride=np.int64(SAMPLE), image_sample=img[::SAMPLE, ::SAMPLE].copy(),
+               sample_stride=np.int64(sample), image_sample=img[::sample, ::sample].copy(),
                # spot checks that pin the (builder) inputs too
                maskFT_abs_sum=np.float64(np.abs(d["maskFT"]).sum(dtype=np.float64)),
-               maskFT_sample=d["maskFT"][::SAMPLE, ::SAMPLE].copy(),
-               pupil_nnz=np.int64((d["pupil"] != 0).sum()), pupil_sample=d["pupil"][::SAMPLE, ::SAMPLE].copy(),
+               maskFT_sample=d["maskFT"][::sample, ::sample].copy(),
+               pupil_nnz=np.int64((d["pupil"] != 0).sum()), pupil_sample=d["pupil"][::sample, ::sample].copy(),
                ls_rows=np.argwhere(d["lightsource"] != 0).astype(np.int32))
     if full_image:
         out.update(image=img, maskFT=d["maskFT"], pupil=d["pupil"])
@@ -191,4 +199,4 @@ if __name__ == "__main__":
         elif w == "cfg5_subset":
             make_cfg_subset("cfg5", 3, 32)
         else:
-            make_cfg(w, full_image=(w == "cfg1"))
+            make_cfg(w, full_image=(w == "cfg1"), sample=32 if w == "cfg5" else SAMPLE)
