@@ -711,7 +711,9 @@ int litho_plan_create_lines(int pn, int N, const int* bbox, int lines, int flags
         // TMA-staged column kernel where the shape has one (M <= 1024).  LITHO_TMA=0 selects plain loads,
         // LITHO_COL_NARROW=0/1 the wide (one 512-thread CTA per SM) or narrow (two 256-thread CTAs) tile.
         {
-            int narrow = LITHO_DEFAULT_COL_NARROW;
+            // measured (profiles/README.md, r02f/r02g): narrow wins at M = 1024 (+3.8 %) and M = 128 (+9 %),
+            // wide at M = 512 (+3.5 %)
+            int narrow = LITHO_DEFAULT_COL_NARROW && Mf != 512;
             if (const char* env = getenv("LITHO_COL_NARROW")) narrow = atoi(env) != 0;
             const int wide_c = dispatch_fast_tma_cols(Mf, p->ppt, 0), narrow_c = dispatch_fast_tma_cols(Mf, p->ppt, 1);
             p->tma_cols = (narrow && narrow_c > 0) ? narrow_c : wide_c;
