@@ -2,6 +2,8 @@
 # Sanitizer passes over the kernel bodies.
 #   scripts/sanitize.sh ubsan   CPU: the emulation build (same kernel bodies + the host side of the C ABI) compiled with
 #                               -fsanitize=undefined, whole emulation test file under halt_on_error (no GPU needed)
+#   scripts/sanitize.sh order   CPU: the emulation suite with the threads of a CTA run in reverse and in pseudo-random order
+#                               between barriers (LITHO_EMU_ORDER): a missing barrier makes the result order-dependent
 #   scripts/sanitize.sh gpu     B200: compute-sanitizer memcheck / racecheck / synccheck on the small GPU parity cases
 #                               (shared-memory exchange, TMA tile buffer + mbarrier, named barriers)
 set -e
@@ -21,6 +23,11 @@ ubsan)
     cp $OUT/liblitho_emu.so $ROOT/tests/emu/liblitho_emu.so
     LD_PRELOAD=$(g++ -print-file-name=libubsan.so) UBSAN_OPTIONS=print_stacktrace=1:halt_on_error=1 \
         python -m pytest $ROOT/tests/test_emu_kernels.py -x -q
+    ;;
+order)
+    for o in reverse random; do
+        LITHO_EMU_ORDER=$o python -m pytest $ROOT/tests/test_emu_kernels.py -x -q
+    done
     ;;
 gpu)
     for tool in memcheck racecheck synccheck; do

@@ -137,11 +137,29 @@ void run_cta(int nthreads, int bx, int by, int bz, int gdx, Body body) {
     }
     bool any = true;
     int idle_sweeps = 0;
+    static const int order = []() {
+        const char* e = getenv("LITHO_EMU_ORDER");
+        return !e ? 0 : (!strcmp(e, "reverse") ? 1 : (!strcmp(e, "random") ? 2 : 0));
+    }();
+    // a stride coprime with the thread count visits every thread once per sweep
+    unsigned stride = 1;
+    if (order == 2) {
+        auto gcd = [](unsigned a, unsigned b) { while (b) { unsigned r = a % b; a = b; b = r; } return a; };
+        for (stride = (unsigned)nthreads / 2 + 1; gcd(stride, (unsigned)nthreads) != 1; ++stride) {}
+    }
+    unsigned sweep = 0;
     while (any) {
         any = false;
         const long before = s.progress;
         int finished = 0;
-        for (int t = 0; t < nthreads; ++t) {
+        // Order in which the threads of the CTA run between two barriers: ascending by default; LITHO_EMU_ORDER =
+        // reverse | random makes a missing barrier (a result that depends on who runs first) show up as a
+        // wrong answer in the parity tests.
+        ++sweep;
+        for (int i = 0; i < nthreads; ++i) {
+            int t = i;
+            if (order == 1) t = nthreads - 1 - i;
+            else if (order == 2) t = (int)(((unsigned long long)i * stride + (unsigned long long)sweep * 7919u) % (unsigned)nthreads);
             if (s.fibers[t].done) continue;
             s.current = t;
             swapcontext(&s.main_uc, &s.fibers[t].uc);
