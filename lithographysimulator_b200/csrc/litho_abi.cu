@@ -116,17 +116,22 @@ struct ExtParams {
 template <class Ctx>
 LITHO_HD void ext_body(const ExtParams& P, const Ctx& ctx) {
     for (int k = 0; k < P.lines; ++k) {
-        if (P.r0 + k > P.r1 - k && k > 0) break;
         int* e = P.ext + 8 * k;
         const int ra = P.r0 + k, rb = P.r1 - k, ca = P.c0 + k, cb = P.c1 - k;
-        if (rb < 0 || cb < 0 || ra >= P.pn || ca >= P.pn) break;
+        // rows and columns run out independently (a 1 x 35 window still has three column lines per side)
+        const bool rows = ra >= 0 && rb < P.pn && (k == 0 || ra <= P.r1) && (k == 0 || rb >= P.r0);
+        const bool cols = ca >= 0 && cb < P.pn && (k == 0 || ca <= P.c1) && (k == 0 || cb >= P.c0);
         for (int i = ctx.tid(); i < P.pn; i += ctx.bdim()) {
-            const cplx a = P.pupil[(size_t)ra * P.pn + i], b = P.pupil[(size_t)rb * P.pn + i];
-            const cplx c = P.pupil[(size_t)i * P.pn + ca], d = P.pupil[(size_t)i * P.pn + cb];
-            if (a.x != 0.f || a.y != 0.f) { atomic_min_i(e + 0, i); atomic_max_i(e + 1, i); }
-            if (b.x != 0.f || b.y != 0.f) { atomic_min_i(e + 2, i); atomic_max_i(e + 3, i); }
-            if (c.x != 0.f || c.y != 0.f) { atomic_min_i(e + 4, i); atomic_max_i(e + 5, i); }
-            if (d.x != 0.f || d.y != 0.f) { atomic_min_i(e + 6, i); atomic_max_i(e + 7, i); }
+            if (rows) {
+                const cplx a = P.pupil[(size_t)ra * P.pn + i], b = P.pupil[(size_t)rb * P.pn + i];
+                if (a.x != 0.f || a.y != 0.f) { atomic_min_i(e + 0, i); atomic_max_i(e + 1, i); }
+                if (b.x != 0.f || b.y != 0.f) { atomic_min_i(e + 2, i); atomic_max_i(e + 3, i); }
+            }
+            if (cols) {
+                const cplx c = P.pupil[(size_t)i * P.pn + ca], d = P.pupil[(size_t)i * P.pn + cb];
+                if (c.x != 0.f || c.y != 0.f) { atomic_min_i(e + 4, i); atomic_max_i(e + 5, i); }
+                if (d.x != 0.f || d.y != 0.f) { atomic_min_i(e + 6, i); atomic_max_i(e + 7, i); }
+            }
         }
     }
 }

@@ -63,7 +63,7 @@ def test_emu_fast_path_dense_window(pn, ps, win):
     assert O.rel_l2(fast, gen) < H.TOL
 
 
-@pytest.mark.parametrize("wr,wc", [(34, 34), (35, 35), (35, 33), (31, 34), (33, 35)])
+@pytest.mark.parametrize("wr,wc", [(34, 34), (35, 35), (35, 33), (31, 34), (33, 35), (1, 35), (34, 2)])
 @pytest.mark.parametrize("tma", ["1", "0"])
 def test_emu_fast_path_window_beyond_even_fit(monkeypatch, wr, wc, tma):
     """Windows of M+2 / M+3 samples (M = 32), as the reference's fp16 pupil grid produces at pn = 8192 (support
@@ -85,6 +85,8 @@ def test_emu_fast_path_window_beyond_even_fit(monkeypatch, wr, wc, tma):
     for (d0, d1), wi in zip(shifts, w):
         ref += wi * np.abs(O.calculate_fft_aerial(np.roll(pup, (d0, d1), (0, 1)), mft, pn, 256)) ** 2
     assert O.rel_l2(fast, ref) < H.TOL
+    if min(wr, wc) < 30:
+        return
     # sparse rim lines (only a short stretch populated, like a disc's edge) with measured extents
     pup2 = pup.copy()
     pup2[r0, :] = 0; pup2[r0, c0 + 10:c0 + 15] = 1 + 1j
