@@ -6,12 +6,13 @@
 One "step" = one full aerial image: abbeImage(fft=True) over all source points of the config
 (mask spectrum and pupil are inputs, as in the reference's call).  Prints ONE JSON line.
 
-  value        images/s with inputs resident in HBM, timed with CUDA events per step, L2 flushed
-               between steps, max over ranks.  N > 1: the source points are sharded across ranks and
-               the partial intensity planes are summed with one NCCL all-reduce per image, so the job
-               is ONE image computed N-way ("scaling": "strong").
-  e2e          same metric through the public API with HOST (pinned) tensors: H2D of mask spectrum,
-               pupil and source, compute, D2H of the image, all inside the timed region.
+  value        images/s with inputs resident in HBM, CUDA events around the K timed images, L2 flushed between
+               images, max over ranks.  N > 1: the source points are sharded across ranks and the partial
+               intensity planes are summed with one NCCL reduce per image (to a root that rotates with the image
+               index, which alone post-processes it), so the job is ONE image computed N-way ("scaling": "strong").
+  e2e          same metric through the public API with HOST (pinned) tensors: H2D of mask spectrum, pupil and
+               source, source-point extraction, compute, D2H of the image, all inside the timed region; the
+               copies of image i+1 overlap the kernels of image i (AbbeEngine.prepare / run).
   roofline     dominant kernel (column pass) timed alone with CUDA events on its stream; algorithmic
                flops per SURVEY.md section 8d; FP32 peak measured in this run by an FMA probe.
   cpu_baseline the oracle (numpy port of the reference algorithm) on a bounded sample of source
