@@ -1,13 +1,20 @@
 #!/bin/bash
-# First GPU call of the next round (one B200): the checks that were prepared at the end of round 1 without GPU time left.
-#   1. full cfg4 / cfg5 images against the reference's (tests/golden/cfg4.npz, cfg5.npz) -- then drop the LITHO_FULL_GOLDEN gate
+# First GPU call of round 2 (one B200): the checks prepared at the end of round 1.
+#   1. full cfg4 / cfg5 images against the reference's (tests/golden/cfg4.npz, cfg5.npz)
 #   2. compute-sanitizer memcheck/racecheck/synccheck on the small parity cases
-#   3. the stock torch/cuFFT library baseline of the hot loop next to the product
-# Usage: gpurun --timeout 1500 -- 'bash scripts/gpu_next.sh'
+#   3. default bench (now with library_baseline = the unmodified reference on device='cuda', parity vs golden)
+#   4. f2 evidence: direct solver FP32 vs tensor-core GEMM proxies
+# Usage: gpurun --timeout 2400 -- 'bash scripts/gpu_next.sh r03a'
+TAG=${1:-r03a}
 mkdir -p gpurun_out
-LITHO_FULL_GOLDEN=1 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "full_cfg4_cfg5" > gpurun_out/next_full_golden.log 2>&1
-echo "full goldens: exit $?"; tail -3 gpurun_out/next_full_golden.log
-timeout 900 bash scripts/sanitize.sh gpu > gpurun_out/next_sanitizer.log 2>&1
-echo "compute-sanitizer: exit $?"; tail -3 gpurun_out/next_sanitizer.log
-timeout 300 python scripts/torch_baseline.py --config cfg3 --points 64 > gpurun_out/next_torch_baseline.log 2>&1
-tail -1 gpurun_out/next_torch_baseline.log
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${TAG}_gpu.txt 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_gpu_tests.log 2>&1
+echo "pytest exit $?" | tee -a gpurun_out/${TAG}_gpu_tests.log; tail -4 gpurun_out/${TAG}_gpu_tests.log
+timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/${TAG}_bench.log 2>&1
+echo "bench exit $?"; tail -c 4000 gpurun_out/${TAG}_bench.log
+timeout 400 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/${TAG}_bench_ref.log 2>&1
+echo "bench ref exit $?"; tail -c 1500 gpurun_out/${TAG}_bench_ref.log
+timeout 300 python scripts/direct_bench.py > gpurun_out/${TAG}_direct.log 2>&1
+echo "direct exit $?"; tail -c 3000 gpurun_out/${TAG}_direct.log
+timeout 900 bash scripts/sanitize.sh gpu > gpurun_out/${TAG}_sanitizer.log 2>&1
+echo "compute-sanitizer: exit $?"; tail -5 gpurun_out/${TAG}_sanitizer.log

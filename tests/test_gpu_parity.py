@@ -507,8 +507,6 @@ def test_largest_grids_against_reference_subset_golden(L, dev, golden_dir, name)
     assert abs(float((img.double() ** 2).sum()) / float(z["img_sumsq"]) - 1) < 2e-5
 
 
-@pytest.mark.skipif(__import__("os").environ.get("LITHO_FULL_GOLDEN") != "1",
-                    reason="full cfg4/cfg5 goldens: generated at the end of round 1, first GPU run pending (LITHO_FULL_GOLDEN=1)")
 @pytest.mark.parametrize("name", ["cfg4", "cfg5"])
 def test_full_cfg4_cfg5_against_reference_golden(L, dev, golden_dir, name):
     """The complete BASELINE cfg4 (4104 source points) and cfg5 (980 points, first focus value) images against the
