@@ -7,17 +7,23 @@ One "step" = one full aerial image: abbeImage(fft=True) over all source points o
 (mask spectrum and pupil are inputs, as in the reference's call).  Prints ONE JSON line.
 
   value        images/s with inputs resident in HBM, CUDA events around the K timed images, L2 flushed between
-               images, max over ranks.  N > 1: the source points are sharded across ranks and the partial
-               intensity planes are summed with one NCCL reduce per image (to a root that rotates with the image
-               index, which alone post-processes it), so the job is ONE image computed N-way ("scaling": "strong").
+               images, max over ranks.  N > 1: the source points are sharded across ranks; the rank that
+               post-processes image i (i mod N) sums the partial intensity planes of all ranks with loads over
+               NVLink from their CUDA-IPC-mapped buffers (litho_peer_sum; --reduce nccl: one ncclReduce instead),
+               so the job is ONE image computed N-way ("scaling": "strong").
   e2e          same metric through the public API with HOST (pinned) tensors: H2D of mask spectrum, pupil and
                source, source-point extraction, compute, D2H of the image, all inside the timed region; the
-               copies of image i+1 overlap the kernels of image i (AbbeEngine.prepare / run).
+               copies of image i+1 overlap the kernels of image i (AbbeEngine.prepare / ShardedPipeline.submit).
   roofline     dominant kernel (column pass) timed alone with CUDA events on its stream; algorithmic
                flops per SURVEY.md section 8d; FP32 peak measured in this run by an FMA probe.
-  cpu_baseline the oracle (numpy port of the reference algorithm) on a bounded sample of source
-               points on this box's host cores, extrapolated linearly in n_src (the loop is strictly
-               per source point, reference imageformation.py:62-67).
+  parity       rel-L2 of the timed loop's last image against the unmodified reference's image of the same config
+               (tests/golden/<cfg>.npz).
+  cpu_baseline the UNMODIFIED reference (oracle/_ref, staged by oracle/build_ref.py) abbeImage(fft=True) on CPU
+               tensors, all host threads, on two sub-sources of the config (slope = cost per source point, the
+               loop is strictly per source point, reference imageformation.py:62-67); the numpy port of the
+               oracle only where oracle/_ref is not staged.
+  library_baseline  the same unmodified reference handed device='cuda': stock ATen + cuFFT on the same B200.
+  --impl reference  the reference arm: that CPU run alone, same config string, JSON line with "impl": "reference".
 """
 from __future__ import annotations
 
@@ -326,93 +332,53 @@ def run_ours(args):
     plan = eng.plan(pn, N, support, generic=True) if args.generic else eng.plan_for(pn, N, support, shifts_all)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    def reduce_fn(inten):
-        if world > 1:
-            dist.all_reduce(inten)
-
-    # Two intensity planes: the reduce + post-processing of image i run on a second stream while the
-    # accumulation of image i+1 proceeds on the main one (throughput mode; --no-pipeline serialises them).
-    fin_stream = torch.cuda.Stream(dev)
-    planes = [eng.intensity_plane(plan) for _ in range(2)]
-    fin_done = [None, None]
-    reduce_work = [None, None]
-    state = {"i": 0, "img": None}
+    # Pipelined, sharded imager (lithographysimulator_b200.distributed.ShardedPipeline): image i is accumulated by
+    # all ranks together; rank i mod N sums the partial planes -- over peer memory (NVLink loads, litho_peer_sum)
+    # unless --reduce nccl -- and alone post-processes it on a second stream while every rank already accumulates
+    # image i+1.  All buffers of a step are allocated up front.
+    from lithographysimulator_b200.distributed import ShardedPipeline
+    pipe = ShardedPipeline(eng, plan, eps, reduce=args.reduce)
+    fin_stream = pipe.fin_stream
 
     def one_image(prep=None, out_host=None):
         """One aerial image.  prep = None: inputs resident in HBM (`value`); otherwise a PreparedImage staged from
         pinned host tensors by eng.prepare() on the copy stream (`e2e`), and the root copies the image to out_host."""
-        i = state["i"]
-        state["i"] += 1
-        inten = planes[i % 2]
-        main = torch.cuda.current_stream(dev)
-        if reduce_work[i % 2] is not None:
-            reduce_work[i % 2].wait()              # the reduce of image i-2 has read this plane
-        if fin_done[i % 2] is not None:
-            main.wait_event(fin_done[i % 2])       # image i-2 has left this plane
-        inten.zero_()
-        if prep is None:
-            eng.accumulate(plan, mft_d, pf_d, shifts_mine, inten, None, args.batch, inputs_ready=not args.no_chain)
-        else:
-            main.wait_event(prep.ready)
-            prep.shifts.record_stream(main)
-            eng.accumulate(prep.plan, prep.maskFT, prep.pupil, prep.shifts, inten, None, args.batch)
-            eng.consumed(prep)                      # the staging set may be refilled once this has run
         if args.no_pipeline:
-            reduce_fn(inten)
-            state["img"] = eng.finalize(plan, inten, eps)
+            inten = pipe.planes[0]
+            inten.zero_()
+            if prep is None:
+                eng.accumulate(plan, mft_d, pf_d, shifts_mine, inten, None, args.batch)
+            else:
+                torch.cuda.current_stream(dev).wait_event(prep.ready)
+                eng.accumulate(prep.plan, prep.maskFT, prep.pupil, prep.shifts, inten, None, args.batch)
+                eng.consumed(prep)
+            if world > 1:
+                dist.all_reduce(inten)
+            pipe.last_image = eng.finalize(plan, inten, eps)
             if out_host is not None:
-                out_host.copy_(state["img"], non_blocking=True)
+                out_host.copy_(pipe.last_image, non_blocking=True)
             return
-        # one NCCL sum-reduce of the partial planes to a root that rotates with the image index, so the
-        # post-processing of consecutive images is spread over the ranks instead of repeated on all of them
-        root = i % world
-        work = None
-        if world > 1:
-            # asynchronous: the main stream goes straight on to the next image; only the post-processing
-            # stream (and the later reuse of this plane) waits for the reduce
-            work = dist.reduce(inten, dst=root, async_op=True)
-        reduce_work[i % 2] = work
-        if rank != root:
-            return
-        ready = torch.cuda.Event()
-        ready.record(main)
-        with torch.cuda.stream(fin_stream):
-            fin_stream.wait_event(ready)
-            if work is not None:
-                work.wait()                         # fin_stream waits for the NCCL reduce
-            state["img"] = eng.finalize(plan, inten, eps)
-            if out_host is not None:
-                out_host.copy_(state["img"], non_blocking=True)   # D2H of the result, off the compute stream
-            done = torch.cuda.Event()
-            done.record(fin_stream)
-            fin_done[i % 2] = done
+        if prep is None:
+            pipe.submit(mft_d, pf_d, shifts_mine, batch=args.batch, inputs_ready=not args.no_chain)
+        else:
+            prep.shifts.record_stream(torch.cuda.current_stream(dev))
+            pipe.submit(prep.maskFT, prep.pupil, prep.shifts, batch=args.batch, wait_event=prep.ready,
+                        on_accumulated=lambda: eng.consumed(prep), out_host=out_host)
 
     def join():
-        for w in reduce_work:
-            if w is not None:
-                w.wait()
-        torch.cuda.current_stream(dev).wait_stream(fin_stream)
+        pipe.join()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # NCCL sets up its channels per (collective, root) on first use: touch every root once, outside the timed
-    # region and whatever --warmup is, so that the rotating-root reduce is warm for all of them
-    if world > 1:
-        for r in range(world):
-            dist.reduce(planes[0], dst=r)
-        planes[0].zero_()
-    # ... and every rank post-processes one image now: with a rotating root a rank's first finalize (workspace
-    # allocation, lazy loading of those kernels) would otherwise land inside a short timed region
-    eng.finalize(plan, planes[0], eps)
-    torch.cuda.synchronize(dev)
     warm = max(args.warmup, 3)   # timing rules: at least 3 warm-up steps
-    for _ in range(warm):
+    for _ in range(max(warm, world)):   # ... and every rank is the root of at least one warm-up image
         one_image()
     join()
     barrier()
+    pipe.check()
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -447,8 +413,8 @@ def run_ours(args):
         z = np.load(gpath)
         st = int(z["sample_stride"])
         ref_s = torch.from_numpy(z["image_sample"]).to(dev)
-        if state["img"] is not None and tuple(state["img"][::st, ::st].shape) == tuple(ref_s.shape):
-            pv[0] = (state["img"][::st, ::st] - ref_s).norm().double() / ref_s.norm().double()
+        if pipe.last_image is not None and tuple(pipe.last_image[::st, ::st].shape) == tuple(ref_s.shape):
+            pv[0] = (pipe.last_image[::st, ::st].double() - ref_s.double()).norm() / ref_s.double().norm()
         if world > 1:
             dist.all_reduce(pv, op=dist.ReduceOp.MAX)   # every rank that post-processed a timed image reports
         if float(pv.item()) >= 0:
@@ -456,6 +422,33 @@ def run_ours(args):
                       "golden": f"tests/golden/{cfg.name}.npz (unmodified reference on CPU, every {st}th pixel)",
                       "image": "last image(s) of the timed loop (chained, pipelined path)"}
             assert parity["rel_l2_vs_reference_golden"] < 1e-5, parity
+
+    # ---- optional per-image event trace of an extra, untimed loop (all ranks; --trace) ----
+    trace = None
+    if args.trace:
+        barrier()
+        pipe.trace = []
+        for _ in range(args.steps):
+            flush.fill_(1)
+            one_image()
+        join()
+        barrier()
+        mine_tr = pipe.trace_ms()
+        pipe.trace = None
+        if world > 1:
+            allt = [None] * world
+            dist.all_gather_object(allt, mine_tr)
+        else:
+            allt = [mine_tr]
+        if rank == 0:
+            acc = [[t["accumulated"] - t["begin"] for t in r] for r in allt]
+            roots = [t for r in allt for t in r if "finalized" in t]
+            trace = {"accumulate_ms_per_rank_mean": [float(np.mean(a)) for a in acc],
+                     "accumulate_ms_max": float(np.max(acc)), "accumulate_ms_min": float(np.min(acc)),
+                     "image_period_ms_per_rank": [float((r[-1]["begin"] - r[0]["begin"]) / max(1, len(r) - 1)) for r in allt],
+                     "root_wait_for_peers_plus_sum_ms": [round(t["summed"] - t["fin_begin"], 4) for t in roots],
+                     "root_finalize_ms": [round(t["finalized"] - t["summed"], 4) for t in roots],
+                     "root_lag_fin_begin_after_accumulated_ms": [round(t["fin_begin"] - t["accumulated"], 4) for t in roots]}
 
     # ---- phase breakdown of one image (events on the current stream, after the timed region) ----
     def timed(fn, reps=3):
@@ -472,7 +465,6 @@ def run_ours(args):
     breakdown = {
         "zero_plane": timed(lambda: inten_b.zero_()),
         "accumulate": timed(lambda: eng.accumulate(plan, mft_d, pf_d, shifts_mine, inten_b, None, args.batch)),
-        "all_reduce": timed(lambda: reduce_fn(inten_b)) if world > 1 else 0.0,
         "finalize": timed(lambda: eng.finalize(plan, inten_b, eps)),
     }
 
@@ -536,11 +528,9 @@ def run_ours(args):
         join()
         torch.cuda.synchronize(dev)
 
-    state["i"] = 0
-    e2e_loop(max(2, min(world, 8)))   # warm-up: staging sets, the upload communicator, every reduce root
-    barrier()
+    e2e_loop(2 * max(1, min(world, 8)))   # warm-up: staging sets, the upload communicator, every root (even count:
+    barrier()                             # the image counter keeps its slot parity)
     e2e_steps = max(2, min(args.steps, 8))
-    state["i"] = 0
     t0 = time.perf_counter()
     e2e_loop(e2e_steps)
     barrier()
@@ -555,11 +545,11 @@ def run_ours(args):
     d2h = out_p[0].numel() * 4
     # the image that came back over PCIe must be the image the resident-input path produced
     e2e_check = None
-    if rank == (e2e_steps - 1) % world and state["img"] is not None:
-        ref_img = eng.abbe_fft(mft_d, pf_d, ls_d, cfg.pixel_size, 4 / pn, cfg.wavelength, plan=plan) if world == 1 else None
-        got = out_p[(e2e_steps - 1) % 2]
-        if ref_img is not None:
-            e2e_check = float((got.to(dev) - ref_img).norm() / ref_img.norm())
+    if world == 1 and pipe.last_image is not None:
+        ref_img = eng.abbe_fft(mft_d, pf_d, ls_d, cfg.pixel_size, 4 / pn, cfg.wavelength, plan=plan).double()
+        got = out_p[(e2e_steps - 1) % 2].to(dev).double()     # float64 norms: the raw intensities are ~1e17
+        e2e_check = float((got - ref_img).norm() / ref_img.norm())
+    pipe.check()
 
     if rank == 0:
         fl_alg = algorithmic_flops(pn, N, n_mine)
@@ -629,7 +619,8 @@ def run_ours(args):
                                "abbeImage(fft=True, device=cuda): stock ATen + cuFFT on the same B200, inputs from the "
                                "reference's own builders", "sample": f"sub-sources of {n_lo} and {n_hi} of the {n_src} source "
                                f"points, image time = intercept + slope*n_src, {len(vals)} repeats, {spent:.1f} s",
-                               "rel_l2_product_vs_library_same_sub_source": float((ours_sub - ref_img).norm() / ref_img.norm())}
+                               "rel_l2_product_vs_library_same_sub_source":
+                                   float((ours_sub.double() - ref_img.double()).norm() / ref_img.double().norm())}
                 except Exception as e:   # the baseline is a reported number, never a reason to lose the bench line
                     library = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -639,11 +630,14 @@ def run_ours(args):
                            "l2": "flushed (256 MB write) between images, inside the timed region", "batch": batch,
                            "pipeline": "sequential, all-reduce, every rank post-processes" if args.no_pipeline else
                            "post-processing of image i overlaps the accumulation of image i+1 (2 streams); with N>1 "
-                           "the partial planes are sum-reduced to rank i mod N, which alone post-processes image i",
+                           "rank i mod N sums the partial planes and alone post-processes image i",
                            "subfft": plan.M, "residues": plan.R,
                            "path": "fast coarse-grid (2 FFTs of length M per line, spectral interpolation once per image)"
-                           if plan.path == 2 else "generic fine-grid", "sharding": f"source points interleaved over {world} rank(s), "
-                                                                           "one NCCL sum-reduce of the intensity plane per image"},
+                           if plan.path == 2 else "generic fine-grid",
+                           "sharding": f"source points interleaved over {world} rank(s)" + ("" if world == 1 else (
+                               "; partial planes summed in rank order by the root with loads over NVLink from the peers' "
+                               "CUDA-IPC-mapped planes (litho_peer_sum), sequence flags instead of a collective"
+                               if pipe.reduce == "peer" else "; one ncclReduce of the intensity plane per image"))},
                 "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
                 "e2e": {"value": 1.0 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": e2e_steps, "rel_l2_vs_resident_path": e2e_check,
@@ -655,6 +649,8 @@ def run_ours(args):
                 "roofline": roofline, "cpu_baseline": cpu, "library_baseline": library, "parity": parity,
                 "breakdown_ms": breakdown,
                 "wall_s_timed_region": t_wall}
+        if trace is not None:
+            line["trace"] = trace
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -675,6 +671,9 @@ def main():
     ap.add_argument("--full-upload", action="store_true", help="e2e, N>1: every rank uploads the full inputs over PCIe")
     ap.add_argument("--no-chain", action="store_true", help="row pass of image i+1 waits for image i's last column pass")
     ap.add_argument("--no-pipeline", action="store_true", help="finalize each image before starting the next")
+    ap.add_argument("--trace", action="store_true", help="extra untimed loop with per-image CUDA events on every rank")
+    ap.add_argument("--reduce", default="peer", choices=["peer", "nccl"],
+                    help="N>1: sum of the partial planes by peer-memory loads on the root (default) or ncclReduce")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -13,7 +13,9 @@
  *   - calls are asynchronous on `stream` (a cudaStream_t passed as void*) unless stated;
  *   - the caller owns every buffer including the workspace; a plan owns only its twiddle table;
  *   - return 0 on success, non-zero on error with a message in litho_last_error();
- *   - re-entrant per plan/stream pair.
+ *   - thread safety: entry points are re-entrant for DIFFERENT plans; a plan carries per-call state of its
+ *     own (its T-ring events, an auxiliary stream, error words) and must be used by one stream / one host
+ *     thread at a time -- create one plan per concurrent stream.
  */
 #ifndef LITHO_B200_H
 #define LITHO_B200_H
@@ -87,6 +89,11 @@ int litho_plan_create_lines(int pn, int N, const int* support, int lines, int fl
 void litho_plan_destroy(litho_plan_t* plan);
 int litho_plan_get_info(const litho_plan_t* plan, litho_plan_info_t* info);
 size_t litho_plan_workspace_bytes(const litho_plan_t* plan, int batch);
+/* Sticky error words of a fast plan, read and cleared (synchronises `stream`): status_host[0] != 0: a source shift lay
+ * outside plan_info.shift_range and was clamped (the images accumulated since the last query are WRONG: use a
+ * LITHO_PLAN_GENERIC plan for sources that wrap the pupil window); status_host[1] != 0: a TMA tile copy of the
+ * column pass never completed (results invalid).  Both stay 0 in correct use. */
+int litho_plan_status(const litho_plan_t* plan, int* status_host, void* stream);
 /* Columns per tile of the TMA-staged column-pass kernel this plan launches (the T tile of the next source
  * point is copied global -> shared by cp.async.bulk.tensor while the current FFT runs); 0 when the plan
  * uses the plain-load column kernel (generic path, sub-FFT > 1024, LITHO_TMA=0, or a driver without
@@ -109,7 +116,10 @@ int litho_abbe_fft_accumulate(const litho_plan_t* plan, const void* maskFT, cons
  * LITHO_PHASE_INPUTS_READY (bit 2): maskFT, pupil and shifts are already valid on the device when the call is
  * made (not produced by work still queued on `stream`).  The row pass of this call may then start while
  * earlier work on `stream` (typically the last column pass of the previous image on the same plan and
- * workspace) is still running; the column passes and the intensity plane stay ordered on `stream`. */
+ * workspace) is still running; the column passes and the intensity plane stay ordered on `stream`.
+ * The flag also promises that NOTHING ELSE has used `workspace` since this plan's previous accumulate call on it
+ * (give every plan that is driven this way a workspace of its own, as AbbeEngine does): the row pass of this
+ * call only waits for this plan's own column passes that last read each T-ring slot. */
 #define LITHO_PHASE_INPUTS_READY 4
 int litho_abbe_fft_accumulate_ex(const litho_plan_t* plan, const void* maskFT, const void* pupil,
                                  const int32_t* shifts, const float* weights, int n_src, int batch,
@@ -167,6 +177,32 @@ int litho_source_build(int pn, double sigma_in, double sigma_out, double shift_x
  * the reference's in-place defocus rescale aberrations[4] *= NA^2/(4*lambda), pupil.py:91-92).
  * pupil / wavefront: pn x pn complex64 outputs, either may be NULL.  Synchronises `stream`. */
 int litho_pupil_build(const float* aberrations_host, int n_ab, int pn, void* pupil, void* wavefront, void* stream);
+
+/* ---- multi-GPU: sum of the partial intensity planes over peer memory (one process per GPU, one box) ----
+ * The reference's source loop is additive (imageformation.py:62-67), so ranks that each accumulate a shard of the
+ * source points hold partial planes whose sum is the image.  Instead of a collective that every GPU must co-schedule,
+ * the rank that post-processes an image reads the other ranks' planes directly over NVLink (CUDA IPC mappings) and
+ * sums them in rank order -- deterministic -- in one kernel.  Cross-process ordering uses 64-bit sequence flags that
+ * live in the same peer-mapped buffers (st.release.sys / ld.acquire.sys).
+ *   litho_peer_alloc   device buffer (zeroed) that other processes of this box can map; handle = LITHO_PEER_HANDLE_BYTES
+ *                      opaque bytes to send them (e.g. torch.distributed.all_gather_object)
+ *   litho_peer_open    map another process's buffer here; litho_peer_close unmaps; litho_peer_free frees an owned one
+ *   litho_peer_signal  after the work queued on `stream`: *flags[i] = value for i < n (flags may be remote)
+ *   litho_peer_wait    block `stream` until flags[i] >= value for all i < n (flags: n consecutive uint64 in LOCAL
+ *                      memory); after ~20 s it gives up and sets *err (device int, may be NULL) to 1
+ *   litho_peer_sum     out[e] = planes[0][e] + ... + planes[n-1][e], e < elems (16-byte aligned pointers; planes may
+ *                      be remote).  flags/value (optional): every CTA re-acquires flags[r] >= value before loading. */
+#define LITHO_MAX_PEERS 16
+#define LITHO_PEER_HANDLE_BYTES 64
+int litho_peer_alloc(size_t bytes, void** ptr, unsigned char* handle);
+int litho_peer_open(const unsigned char* handle, void** ptr);
+int litho_peer_close(void* ptr);
+int litho_peer_free(void* ptr);
+int litho_peer_signal(void* const* flags, int n, uint64_t value, void* stream);
+int litho_peer_wait(const void* flags, int n, uint64_t value, int* err, void* stream);
+int litho_peer_sum(float* out, const float* const* planes, int n, uint64_t elems, const void* flags, uint64_t value,
+                   int* err, void* stream);
+const char* litho_peer_last_error(void);
 
 /* FP32 FMA throughput probe (roofline denominator measured in the same run): launches `blocks` CTAs
  * of 256 threads, each thread doing iters*16 dependent-chain FMAs; *flops receives the flop count. */

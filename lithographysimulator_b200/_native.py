@@ -48,6 +48,7 @@ SYMBOLS = [
     ("litho_plan_get_info", C.c_int, [_P, C.POINTER(PlanInfo)]),
     ("litho_plan_workspace_bytes", C.c_size_t, [_P, C.c_int]),
     ("litho_plan_column_tile", C.c_int, [_P]),
+    ("litho_plan_status", C.c_int, [_P, C.POINTER(C.c_int), _P]),
     ("litho_abbe_fft_accumulate", C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P, C.c_size_t, _P]),
     ("litho_abbe_fft_accumulate_ex", C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P, C.c_size_t, _P, C.c_int]),
     ("litho_mask_spectrum_workspace_bytes", C.c_size_t, [C.c_int, C.c_double, C.c_int]),
@@ -65,7 +66,17 @@ SYMBOLS = [
     ("litho_abbe_fft_finalize", C.c_int, [_P, _P, C.c_double, _P, _P, C.c_size_t, _P]),
     ("litho_abbe_fft_unpermute", C.c_int, [_P, _P, _P, _P, C.c_size_t, _P]),
     ("litho_fft_field", C.c_int, [_P, _P, _P, _P, _P, C.c_size_t, _P]),
+    ("litho_peer_alloc", C.c_int, [C.c_size_t, C.POINTER(_P), C.c_char_p]),
+    ("litho_peer_open", C.c_int, [C.c_char_p, C.POINTER(_P)]),
+    ("litho_peer_close", C.c_int, [_P]),
+    ("litho_peer_free", C.c_int, [_P]),
+    ("litho_peer_signal", C.c_int, [C.POINTER(_P), C.c_int, C.c_uint64, _P]),
+    ("litho_peer_wait", C.c_int, [_P, C.c_int, C.c_uint64, _P, _P]),
+    ("litho_peer_sum", C.c_int, [_P, C.POINTER(_P), C.c_int, C.c_uint64, _P, C.c_uint64, _P, _P]),
+    ("litho_peer_last_error", C.c_char_p, []),
 ]
+MAX_PEERS = 16           # LITHO_MAX_PEERS
+PEER_HANDLE_BYTES = 64   # LITHO_PEER_HANDLE_BYTES
 
 
 class NativeLib:
@@ -90,6 +101,36 @@ class NativeLib:
         if rc != 0:
             msg = self.litho_last_error()
             raise LithoError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")
+
+    def check_peer(self, rc: int, what: str = ""):
+        if rc != 0:
+            msg = self.litho_peer_last_error()
+            raise LithoError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")
+
+    # ---- peer memory (multi-GPU sum of the partial planes) ------------------------------------
+    def peer_alloc(self, nbytes: int):
+        """(pointer, handle bytes) of a zeroed buffer that the other processes of this box can map."""
+        ptr = _P()
+        handle = C.create_string_buffer(PEER_HANDLE_BYTES)
+        self.check_peer(self.litho_peer_alloc(nbytes, C.byref(ptr), handle), "litho_peer_alloc")
+        return int(ptr.value), bytes(handle.raw)
+
+    def peer_open(self, handle: bytes) -> int:
+        ptr = _P()
+        self.check_peer(self.litho_peer_open(C.create_string_buffer(handle, PEER_HANDLE_BYTES), C.byref(ptr)), "litho_peer_open")
+        return int(ptr.value)
+
+    def peer_signal(self, flag_ptrs, value: int, stream: int = 0):
+        arr = (_P * len(flag_ptrs))(*flag_ptrs)
+        self.check_peer(self.litho_peer_signal(arr, len(flag_ptrs), value, stream), "litho_peer_signal")
+
+    def peer_wait(self, flags_ptr: int, n: int, value: int, err_ptr=None, stream: int = 0):
+        self.check_peer(self.litho_peer_wait(flags_ptr, n, value, err_ptr, stream), "litho_peer_wait")
+
+    def peer_sum(self, out_ptr: int, plane_ptrs, elems: int, flags_ptr=None, value: int = 0, err_ptr=None, stream: int = 0):
+        arr = (_P * len(plane_ptrs))(*plane_ptrs)
+        self.check_peer(self.litho_peer_sum(out_ptr, arr, len(plane_ptrs), elems, flags_ptr, value, err_ptr, stream),
+                        "litho_peer_sum")
 
     # ---- thin typed helpers (pointers are plain ints) --------------------------------------
     def epsilon_n(self, deltaK: float, pixelSize: float, wavelength: float):
@@ -148,6 +189,12 @@ class Plan:
         self.lib.check(self.lib.litho_abbe_fft_accumulate_ex(self.handle, maskFT, pupil, shifts, weights, n_src, batch,
                                                              intensity, workspace, workspace_bytes, stream, phases),
                        "litho_abbe_fft_accumulate")
+
+    def status(self, stream=0):
+        """(shift_clamped, tile_copy_lost) sticky error words of a fast plan, read and cleared (synchronises)."""
+        st = (C.c_int * 2)()
+        self.lib.check(self.lib.litho_plan_status(self.handle, st, stream), "litho_plan_status")
+        return int(st[0]), int(st[1])
 
     def column_tile(self) -> int:
         """Columns per TMA-staged tile of the column pass (0: plain-load column kernel)."""

@@ -115,6 +115,7 @@ struct FastRowsParams {
     int s_begin, batch;
     const cplx* tables;
     cplx* T;  // [batch][2][Sr][M]
+    int* status;  // plan-owned device words: [0] set to 1 when a shift had to be clamped (contract violated)
 };
 
 struct FastColsParams {
@@ -130,6 +131,7 @@ struct FastColsParams {
     int use_tma, nbox, rim;      // boxes per tile; rim: rows u = M .. Sr-1 of the tile (0 .. RIM_LINES), 1-D copies
     long long row_begin;
     const cplx* tables_c;        // compact twiddle tables (TmaShape layout)
+    int* status;                 // plan-owned device words: [1] set to 1 when a tile copy never completed
     TileMap tile;
 };
 
@@ -165,6 +167,7 @@ LITHO_HD void fast_row_load(cplx (&v)[PPT], const FastRowsParams& P, int s, int 
     // memory-safe (the result is then wrong, never out of bounds)
     const int mr = iclamp(P.pr0 + line + sh.x, 0, P.pn - 1);
     const int mc = iclamp(P.pc0 + sh.y, 0, P.pn - P.Sc);
+    if ((mr != P.pr0 + line + sh.x || mc != P.pc0 + sh.y) && g == 0 && P.status) P.status[0] = 1;
     const cplx* mrow = P.mask + (size_t)mr * P.pn + mc;
     const int last = P.Sc - 1;
     const cplx* pg = prow + g;
@@ -480,7 +483,7 @@ LITHO_HD void fast_cols_tma_body(const FastColsParams& P, const Ctx& ctx, unsign
     const int last = P.Sr - 1;
 
     for (int sl = 0; sl < P.batch; ++sl) {
-        ctx.mbar_wait(bar, (unsigned)(sl & 1));
+        if (!ctx.mbar_wait(bar, (unsigned)(sl & 1)) && P.status) P.status[1] = 1;   // results invalid: reported, never silent
         cplx v[PPT];
         if (last >= M - 1) {
 #pragma unroll
@@ -698,31 +701,32 @@ struct RimParams {
     const int2_* shifts;
     const float* weights;
     int n_src;
+    int per_cta;    // source points per CTA (CTA c takes [c*per_cta, (c+1)*per_cta))
     int ext[4][RIM_LINES][2];
     int er, ec;     // -1: no rim lines on that axis
-    float* frow;    // [er+1][2*Sc-1] complex, interleaved
-    float* fcol;    // [ec+1][2*Sr-1] complex
+    float* frow;    // this launch's partial sums: CTA c owns frow + c*stride, [er+1][2*Sc-1] complex, interleaved
+    float* fcol;    // likewise, [ec+1][2*Sr-1] complex
+    size_t stride;  // floats between the slices of consecutive CTAs (0: all CTAs share one slice -- single CTA only)
 };
 
-LITHO_HD void atomic_add_f(float* p, float v) {
-#if defined(__CUDA_ARCH__)
-    atomicAdd(p, v);
-#else
-    *p += v;
-#endif
-}
-
-// one CTA per source point; smem holds the two vectors of the pair being correlated
+// One CTA per chunk of source points, taken in order; every partial sum has exactly one owner thread and is added
+// to the CTA's private slice with plain read-modify-writes, so the result does not depend on scheduling.
+// rim_reduce_body then folds the slices into the plane in chunk order.  smem holds the two vectors of the pair
+// being correlated.
 template <class Ctx>
 LITHO_HD void rim_body(const RimParams& P, const Ctx& ctx, cplx* smem) {
-    const int s = ctx.bx();
+    const int s_lo = ctx.bx() * P.per_cta;
+    const int s_hi = (s_lo + P.per_cta) < P.n_src ? (s_lo + P.per_cta) : P.n_src;
+    float* const frow = P.frow + (size_t)ctx.bx() * P.stride;
+    float* const fcol = P.fcol + (size_t)ctx.bx() * P.stride;
+    for (int s = s_lo; s < s_hi; ++s) {
     const int2_ sh = P.shifts[s];
     const float w = P.weights ? P.weights[s] : 1.f;
     for (int axis = 0; axis < 2; ++axis) {
         const int e = axis == 0 ? P.er : P.ec;
         const int Sfix = axis == 0 ? P.Sr : P.Sc;      // size along the axis the pair is separated on
         const int Slag = axis == 0 ? P.Sc : P.Sr;      // size along the lines
-        float* F = axis == 0 ? P.frow : P.fcol;
+        float* F = axis == 0 ? frow : fcol;
         for (int k = 0; k <= e; ++k) {                 // frequency M + k
             for (int t = 0; t + k <= e; ++t) {         // pair: "lo" line t, "hi" line t + M + k = Sfix-1-b
                 const int b = e - k - t;
@@ -755,12 +759,29 @@ LITHO_HD void rim_body(const RimParams& P, const Ctx& ctx, cplx* smem) {
                     cplx acc = mk(0.f, 0.f);
                     for (int c = c0; c < c1; ++c) acc = cadd(acc, cmul(gh[c + d], cconj(gl[c])));
                     const int n = (hl - ll) + d;
-                    atomic_add_f(Fk + 2 * (n + Slag - 1), w * acc.x);
-                    atomic_add_f(Fk + 2 * (n + Slag - 1) + 1, w * acc.y);
+                    // sole owner of this entry within the CTA (pairs and source points are taken in sequence,
+                    // separated by the CTA barriers above)
+                    Fk[2 * (n + Slag - 1)] += w * acc.x;
+                    Fk[2 * (n + Slag - 1) + 1] += w * acc.y;
                 }
             }
         }
     }
+    }
+}
+
+// plane[j] += slices[0][j] + slices[1][j] + ... in slice order (one thread per float)
+struct RimReduceParams {
+    const float* slices;
+    size_t stride;
+    int n_slices;
+    int n;          // floats per slice that are summed
+    float* plane;
+};
+LITHO_HD void rim_reduce_elem(const RimReduceParams& P, int j) {
+    float acc = 0.f;
+    for (int c = 0; c < P.n_slices; ++c) acc += P.slices[(size_t)c * P.stride + j];
+    P.plane[j] += acc;
 }
 
 // ----------------------------------------------------------------------------- coarse -> fine

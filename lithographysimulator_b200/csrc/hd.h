@@ -201,9 +201,9 @@ struct DevCtx {
                          : "memory");
         }
     }
-    // All threads: wait until the copy announced for this phase has landed.  Bounded: a logic error gives
-    // wrong numbers (caught by the parity tests), never a hung GPU.
-    __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) const {
+    // All threads: wait until the copy announced for this phase has landed.  Bounded (a lost copy must not hang
+    // the GPU); returns false on timeout so that the caller can raise the plan's error word.
+    __device__ __forceinline__ bool mbar_wait(unsigned long long* bar, unsigned phase) const {
         const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
         unsigned ok = 0;
         for (int spins = 0; !ok && spins < (1 << 26); ++spins) {
@@ -215,6 +215,7 @@ struct DevCtx {
                 : "r"(a), "r"(phase)
                 : "memory");
         }
+        return ok != 0;
     }
 };
 #endif

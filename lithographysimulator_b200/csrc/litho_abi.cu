@@ -189,6 +189,10 @@ __global__ void rim_kernel(const __grid_constant__ RimParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     rim_body(P, DevCtx{}, reinterpret_cast<cplx*>(smem_raw));
 }
+__global__ void rim_reduce_kernel(const __grid_constant__ RimReduceParams P) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < P.n) rim_reduce_elem(P, j);
+}
 __global__ void coarse_unperm_kernel(const __grid_constant__ CoarseUnpermParams P) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < 2 * P.M) coarse_unperm_elem(P, blockIdx.y, b);
@@ -279,6 +283,31 @@ static int get_twiddles(int L, cplx** out) {
     return 0;
 }
 
+// --------------------------------------------------------------------------- small persistent scratch
+// The support-analysis entry points (pupil_bbox, pupil_support, shift_bounds, pupil_build) need a few device
+// words each and synchronise anyway; a per-device scratch that lives for the process replaces a cudaMalloc +
+// cudaFree pair per call (cudaFree synchronises the whole device).  The mutex is held for the duration of the call.
+static std::mutex g_scratch_mutex;
+static std::map<int, int*> g_scratch;
+static const size_t SCRATCH_BYTES = 16384;
+static int get_scratch(int** out) {   // call with g_scratch_mutex held
+    int dev = 0;
+#if !defined(LITHO_EMU)
+    if (cudaGetDevice(&dev) != cudaSuccess) return 1;
+#endif
+    auto it = g_scratch.find(dev);
+    if (it != g_scratch.end()) {
+        *out = it->second;
+        return 0;
+    }
+    int* d = nullptr;
+    const int rc = be_malloc((void**)&d, SCRATCH_BYTES);
+    if (rc != 0) return rc;
+    g_scratch[dev] = d;
+    *out = d;
+    return 0;
+}
+
 // --------------------------------------------------------------------------- TMA tile map of the T ring
 // T (any number of [Sr][M] complex64 planes back to back) as a 2-D float32 tensor: 2*M floats per row.
 // The CUtensorMap is encoded through the driver entry point obtained from the runtime (no libcuda link).
@@ -331,6 +360,8 @@ static int make_tile_map(TileMap* tm, const void* base, int M, long long rows, i
 // --------------------------------------------------------------------------- plan
 // T ring slots of the fast path: rows(b) may run LITHO_TSLOTS-1 batches ahead of cols(b)
 #define LITHO_TSLOTS 3
+// CTAs (= private slices) of the rim-sum kernel: each takes a contiguous chunk of the source points in order
+#define LITHO_RIM_CHUNKS 128
 // TMA-staged column pass: narrow tiles (two 256-thread CTAs per SM) or wide ones (one 512-thread CTA)
 #ifndef LITHO_DEFAULT_COL_NARROW
 #define LITHO_DEFAULT_COL_NARROW 1
@@ -363,6 +394,9 @@ struct litho_plan {
     int fused_B;     // source points per group of the fused kernel
     int* counters;   // device: work-queue index, dependency counters, error flag (owned by the plan)
     int counters_cap;
+    int* status;     // device, 4 ints: [0] a shift had to be clamped, [1] a TMA tile copy never completed
+    float* rim_scratch;   // device: LITHO_RIM_CHUNKS private slices of the rim sums (deterministic two-stage sum)
+    size_t rim_stride;    // floats per slice
 #if !defined(LITHO_EMU)
     cudaStream_t aux_stream;  // row passes of the fast path run here, overlapping the column passes
     cudaEvent_t ev_start, ev_rows[LITHO_TSLOTS], ev_cols[LITHO_TSLOTS];
@@ -507,8 +541,9 @@ int litho_epsilon_n(double deltaK, double pixelSize, double wavelength, double* 
 int litho_pupil_bbox(const void* pupil, int pn, int* bbox_host, void* stream) {
     if (!pupil || pn <= 0 || !bbox_host) return fail(LITHO_ERR_ARG, "pupil_bbox: bad argument");
     litho_stream_t st = (litho_stream_t)stream;
+    std::lock_guard<std::mutex> scratch_lock(g_scratch_mutex);
     int* dbox = nullptr;
-    BE_CHECK(be_malloc((void**)&dbox, 4 * sizeof(int)));
+    BE_CHECK(get_scratch(&dbox));
     int init[4] = {pn, -1, pn, -1};
     int rc = be_h2d(dbox, init, sizeof(init), st);
     if (rc == 0) {
@@ -521,7 +556,6 @@ int litho_pupil_bbox(const void* pupil, int pn, int* bbox_host, void* stream) {
 #endif
     }
     if (rc == 0) rc = be_d2h_sync(bbox_host, dbox, 4 * sizeof(int), st);
-    be_free(dbox);
     if (rc != 0) return fail(LITHO_ERR_CUDA, std::string("pupil_bbox: ") + be_errstr(rc));
     if (bbox_host[1] < 0) {
         bbox_host[0] = 0; bbox_host[1] = -1; bbox_host[2] = 0; bbox_host[3] = -1;
@@ -545,8 +579,9 @@ int litho_pupil_support_lines(const void* pupil, int pn, int lines, int* support
         return LITHO_OK;
     }
     litho_stream_t st = (litho_stream_t)stream;
+    std::lock_guard<std::mutex> scratch_lock(g_scratch_mutex);
     int* dext = nullptr;
-    BE_CHECK(be_malloc((void**)&dext, n * sizeof(int)));
+    BE_CHECK(get_scratch(&dext));
     rc = be_h2d(dext, support_host + 4, n * sizeof(int), st);
     if (rc == 0) {
         ExtParams P{(const cplx*)pupil, pn, r0, r1, c0, c1, lines, dext};
@@ -558,7 +593,6 @@ int litho_pupil_support_lines(const void* pupil, int pn, int lines, int* support
 #endif
     }
     if (rc == 0) rc = be_d2h_sync(support_host + 4, dext, n * sizeof(int), st);
-    be_free(dext);
     if (rc != 0) return fail(LITHO_ERR_CUDA, std::string("pupil_support: ") + be_errstr(rc));
     return LITHO_OK;
 }
@@ -569,8 +603,9 @@ int litho_shift_bounds(const int32_t* shifts, int n_src, int* bounds_host, void*
     bounds_host[1] = bounds_host[3] = 0;
     if (n_src == 0) return LITHO_OK;
     litho_stream_t st = (litho_stream_t)stream;
+    std::lock_guard<std::mutex> scratch_lock(g_scratch_mutex);
     int* d = nullptr;
-    BE_CHECK(be_malloc((void**)&d, 4 * sizeof(int)));
+    BE_CHECK(get_scratch(&d));
     int init[4] = {INT32_MAX, INT32_MIN, INT32_MAX, INT32_MIN};
     int rc = be_h2d(d, init, sizeof(init), st);
     if (rc == 0) {
@@ -583,7 +618,6 @@ int litho_shift_bounds(const int32_t* shifts, int n_src, int* bounds_host, void*
 #endif
     }
     if (rc == 0) rc = be_d2h_sync(bounds_host, d, 4 * sizeof(int), st);
-    be_free(d);
     if (rc != 0) return fail(LITHO_ERR_CUDA, std::string("shift_bounds: ") + be_errstr(rc));
     return LITHO_OK;
 }
@@ -637,6 +671,7 @@ int litho_plan_create_lines(int pn, int N, const int* bbox, int lines, int flags
     // ---- fast path eligibility: even window fit S <= Mf+1, coarse grid Nc = 2*Mf no finer than N ----
     p->path = 1; p->tables = nullptr; p->tables_c = nullptr; p->tma_box_rows = 0; p->Mf = p->Nc = p->q = 0; p->er = p->ec = -1;
     p->fused = 0; p->fused_B = 2; p->counters = nullptr; p->counters_cap = 0; p->tma_cols = 0;
+    p->status = nullptr; p->rim_scratch = nullptr; p->rim_stride = 0;
     p->last_ws = nullptr; p->last_batch = 0;
     for (int i = 0; i < LITHO_TSLOTS; ++i) p->cols_recorded[i] = 0;
 #if !defined(LITHO_EMU)
@@ -768,6 +803,24 @@ int litho_plan_create_lines(int pn, int N, const int* bbox, int lines, int flags
             }
         }
         per = (size_t)2 * p->Sr * Mf * sizeof(cplx);
+        // error words + the private slices of the two-stage rim sums (only when rim lines exist)
+        rc = be_malloc((void**)&p->status, 4 * sizeof(int));
+        if (rc == 0) {
+            const int zero[4] = {0, 0, 0, 0};
+            rc = be_h2d(p->status, zero, sizeof(zero), 0);
+        }
+        if (rc == 0 && p->q > 1 && (p->er >= 0 || p->ec >= 0)) {
+            p->rim_stride = (size_t)2 * RIM_LINES * (2 * p->Sc - 1) + (size_t)2 * RIM_LINES * (2 * p->Sr - 1);
+            rc = be_malloc((void**)&p->rim_scratch, (size_t)LITHO_RIM_CHUNKS * p->rim_stride * sizeof(float));
+        }
+#if !defined(LITHO_EMU)
+        if (rc == 0) rc = (int)cudaStreamSynchronize(0);
+#endif
+        if (rc != 0) {
+            const std::string msg = std::string("plan_create: status / rim scratch: ") + be_errstr(rc);
+            litho_plan_destroy(p);
+            return fail(LITHO_ERR_CUDA, msg);
+        }
     }
     // batch (source points per launch pair).  Generic path: T of one batch around 64 MB.  Fast path:
     // measured on B200 at cfg3 (profiles/README.md): per-launch costs (table loads, the read-modify-write of
@@ -786,6 +839,8 @@ void litho_plan_destroy(litho_plan_t* p) {
     if (p->tables) be_free(p->tables);
     if (p->tables_c) be_free(p->tables_c);
     if (p->counters) be_free(p->counters);
+    if (p->status) be_free(p->status);
+    if (p->rim_scratch) be_free(p->rim_scratch);
 #if !defined(LITHO_EMU)
     if (p->aux_stream) {
         cudaStreamSynchronize(p->aux_stream);
@@ -826,6 +881,23 @@ int litho_plan_get_info(const litho_plan_t* p, litho_plan_info_t* info) {
     // shifts for which roll() does not wrap the pupil window (precondition of the fast path)
     info->shift_range[0] = -p->bbox[0]; info->shift_range[1] = p->pn - 1 - p->bbox[1];
     info->shift_range[2] = -p->bbox[2]; info->shift_range[3] = p->pn - 1 - p->bbox[3];
+    return LITHO_OK;
+}
+
+int litho_plan_status(const litho_plan_t* p, int* status_host, void* stream) {
+    if (!p || !status_host) return fail(LITHO_ERR_ARG, "plan_status: null argument");
+    status_host[0] = status_host[1] = 0;
+    if (!p->status) return LITHO_OK;   // generic plans have nothing to report
+    int tmp[4] = {0, 0, 0, 0};
+    BE_CHECK(be_d2h_sync(tmp, p->status, sizeof(tmp), (litho_stream_t)stream));
+    status_host[0] = tmp[0]; status_host[1] = tmp[1];
+    if (tmp[0] || tmp[1]) {
+        const int zero[4] = {0, 0, 0, 0};
+        BE_CHECK(be_h2d(p->status, zero, sizeof(zero), (litho_stream_t)stream));
+#if !defined(LITHO_EMU)
+        BE_CHECK((int)cudaStreamSynchronize((litho_stream_t)stream));
+#endif
+    }
     return LITHO_OK;
 }
 
@@ -944,11 +1016,11 @@ int litho_abbe_fft_accumulate_ex(const litho_plan_t* p, const void* maskFT, cons
         memset(&fr, 0, sizeof(fr));
         fr.pupil = (const cplx*)pupil; fr.mask = (const cplx*)maskFT; fr.pn = p->pn;
         fr.pr0 = p->bbox[0]; fr.pc0 = p->bbox[2]; fr.Sr = p->Sr; fr.Sc = p->Sc;
-        fr.shifts = (const int2_*)shifts; fr.tables = p->tables; fr.T = (cplx*)workspace;
+        fr.shifts = (const int2_*)shifts; fr.tables = p->tables; fr.T = (cplx*)workspace; fr.status = p->status;
         FastColsParams fc;
         memset(&fc, 0, sizeof(fc));
         fc.T = (const cplx*)workspace; fc.Sr = p->Sr; fc.weights = weights; fc.tables = p->tables;
-        fc.ic = intensity;
+        fc.ic = intensity; fc.status = p->status;
         const bool use_fused = p->fused && (phases & 3) == 3 &&
                                workspace_bytes >= 2 * (size_t)p->fused_B * 2 * p->Sr * p->Mf * sizeof(cplx);
         if (use_fused) {
@@ -1057,7 +1129,15 @@ int litho_abbe_fft_accumulate_ex(const litho_plan_t* p, const void* maskFT, cons
             rm.shifts = (const int2_*)shifts; rm.weights = weights; rm.n_src = n_src;
             memcpy(rm.ext, p->ext, sizeof(rm.ext));
             rm.er = p->er; rm.ec = p->ec;
-            rm.frow = rim_row_ptr(p, intensity); rm.fcol = rim_col_ptr(p, intensity);
+            // two stages, no atomics: LITHO_RIM_CHUNKS CTAs each sum a contiguous chunk of source points into a
+            // private slice, then the slices are folded into the plane in chunk order (bit-reproducible)
+            const int chunks = n_src < LITHO_RIM_CHUNKS ? n_src : LITHO_RIM_CHUNKS;
+            rm.per_cta = (n_src + chunks - 1) / chunks;
+            const int ctas = (n_src + rm.per_cta - 1) / rm.per_cta;
+            rm.frow = p->rim_scratch; rm.fcol = p->rim_scratch + rim_row_floats(p); rm.stride = p->rim_stride;
+            RimReduceParams rr;
+            rr.slices = p->rim_scratch; rr.stride = p->rim_stride; rr.n_slices = ctas; rr.n = (int)p->rim_stride;
+            rr.plane = rim_row_ptr(p, intensity);
             // shared memory: the longest (lo, hi) pair of lines that gets correlated
             int longest = 1;
             for (int axis = 0; axis < 2; ++axis) {
@@ -1072,11 +1152,16 @@ int litho_abbe_fft_accumulate_ex(const litho_plan_t* p, const void* maskFT, cons
             }
             const size_t smem = (size_t)longest * sizeof(cplx);
 #if defined(LITHO_EMU)
-            litho_emu::launch(n_src, 1, 1, 64, smem, [&](const litho_emu::EmuCtx& c, char* s) { rim_body(rm, c, (cplx*)s); });
+            memset(p->rim_scratch, 0, (size_t)ctas * p->rim_stride * sizeof(float));
+            litho_emu::launch(ctas, 1, 1, 64, smem, [&](const litho_emu::EmuCtx& c, char* s) { rim_body(rm, c, (cplx*)s); });
+            for (int j = 0; j < rr.n; ++j) rim_reduce_elem(rr, j);
 #else
+            BE_CHECK((int)cudaMemsetAsync(p->rim_scratch, 0, (size_t)ctas * p->rim_stride * sizeof(float), st));
             if (smem > 48 * 1024)
                 BE_CHECK((int)cudaFuncSetAttribute(rim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            rim_kernel<<<n_src, 256, smem, st>>>(rm);
+            rim_kernel<<<ctas, 256, smem, st>>>(rm);
+            BE_CHECK((int)cudaGetLastError());
+            rim_reduce_kernel<<<(rr.n + 255) / 256, 256, 0, st>>>(rr);
             BE_CHECK((int)cudaGetLastError());
 #endif
         }
@@ -1585,7 +1670,16 @@ int litho_pupil_build(const float* aberrations_host, int n_ab, int pn, void* pup
     }
     litho_stream_t st = (litho_stream_t)stream;
     ZernikeTerm* dterms = nullptr;
-    BE_CHECK(be_malloc((void**)&dterms, sizeof(ZernikeTerm) * n_ab));
+    std::unique_lock<std::mutex> scratch_lock(g_scratch_mutex, std::defer_lock);
+    const bool own_terms = sizeof(ZernikeTerm) * (size_t)n_ab > SCRATCH_BYTES;   // > ~200 terms: a buffer of its own
+    if (own_terms) {
+        BE_CHECK(be_malloc((void**)&dterms, sizeof(ZernikeTerm) * n_ab));
+    } else {
+        scratch_lock.lock();
+        int* sc = nullptr;
+        BE_CHECK(get_scratch(&sc));
+        dterms = reinterpret_cast<ZernikeTerm*>(sc);
+    }
     int rc = be_h2d(dterms, terms.data(), sizeof(ZernikeTerm) * n_ab, st);
     PupilParams P;
     memset(&P, 0, sizeof(P));
@@ -1603,7 +1697,7 @@ int litho_pupil_build(const float* aberrations_host, int n_ab, int pn, void* pup
         if (rc == 0) rc = (int)cudaStreamSynchronize(st);  // the term table is freed below
 #endif
     }
-    be_free(dterms);
+    if (own_terms) be_free(dterms);
     if (rc != 0) return fail(LITHO_ERR_CUDA, std::string("pupil_build: ") + be_errstr(rc));
     return LITHO_OK;
 }

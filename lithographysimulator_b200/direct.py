@@ -10,7 +10,7 @@ import ctypes as C
 import torch
 
 from . import _native
-from .imaging import AbbeEngine, _as_c64, source_shifts
+from .imaging import AbbeEngine, _as_c64, _check_square, source_shifts
 
 
 def _operator(lib, pn: int, pixelSize, wavelength: float, sign: int, dev) -> torch.Tensor:
@@ -30,9 +30,11 @@ def direct_abbe_image(maskFT, pupilF, lightsource, pixelSize, wavelength, dev, w
     eng = AbbeEngine.get(dev)
     lib = eng.lib
     with torch.cuda.device(dev):
+        pn = _check_square("maskFT", maskFT)
+        _check_square("pupilF", pupilF, pn)
+        _check_square("lightsource", lightsource, pn)
         maskFT_d = _as_c64(maskFT, dev)
         pupil_d = _as_c64(pupilF, dev)
-        pn = int(maskFT_d.shape[0])
         shifts = source_shifts(lightsource.to(dev), pn)
         n_src = int(shifts.shape[0])
         out = torch.zeros((pn, pn), dtype=torch.float32, device=dev)
@@ -65,9 +67,10 @@ def direct_field(pupil, maskFT, fraunhoferConstant, pixelNumber, pixelSize, dev)
     sign = -1 if const.imag < 0 else 1
     wavelength = 2 * torch.pi / abs(const.imag)
     with torch.cuda.device(dev):
+        pn = _check_square("maskFT", maskFT)
+        _check_square("pupil", pupil, pn)
         maskFT_d = _as_c64(maskFT, dev)
         pupil_d = _as_c64(pupil, dev)
-        pn = int(maskFT_d.shape[0])
         field = torch.zeros((pn, pn), dtype=torch.complex64, device=dev)
         bbox = eng.pupil_bbox(pupil_d)
         if bbox[1] < bbox[0]:

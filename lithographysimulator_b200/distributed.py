@@ -12,7 +12,243 @@ import torch.distributed as dist
 
 from .imaging import AbbeEngine, _as_c64, _require_cuda, epsilon_n, source_shifts
 
-__all__ = ["shard_shifts", "abbe_image_sharded", "focus_sweep_sharded"]
+__all__ = ["shard_shifts", "abbe_image_sharded", "focus_sweep_sharded", "PeerPlanes", "ShardedPipeline",
+           "tensor_from_ptr"]
+
+
+class _DevPtr:
+    """Minimal __cuda_array_interface__ carrier so that torch can view memory this package allocated itself
+    (peer-mapped buffers come from cudaMalloc + CUDA IPC, not from torch's caching allocator)."""
+
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def tensor_from_ptr(ptr: int, n: int, dev, dtype=torch.float32) -> torch.Tensor:
+    typestr = {torch.float32: "<f4", torch.int32: "<i4", torch.int64: "<i8"}[dtype]
+    return torch.as_tensor(_DevPtr(ptr, n, typestr), device=dev)
+
+
+class PeerPlanes:
+    """`slots` partial-intensity planes per rank in memory every rank of the box maps (CUDA IPC), plus a mailbox of
+    64-bit sequence flags, for the peer-memory sum of include/litho_b200.h (litho_peer_*).
+
+    Protocol for image number `seq` (1, 2, ...) in slot k whose root is rank R:
+      every rank   accumulates into plane k, then publish(k, seq, R)          -> arrive[k][rank] on R's mailbox
+      rank R       gather_sum(k, seq, out): waits for all arrive flags, sums the planes of all ranks in rank order
+                   over NVLink into `out`, then writes consumed[k] = seq on every rank's mailbox
+      every rank   wait_consumed(k, seq) before it zeroes / reuses plane k
+    `exchange(obj)` must return the list of every rank's obj (e.g. a torch.distributed.all_gather_object wrapper);
+    the constructor is collective.  Pointers are plain ints, so the same class drives the CPU emulation in the
+    world-size-2 gloo tests."""
+
+    MAILBOX_BYTES = 4096
+
+    def __init__(self, lib, elems: int, rank: int, world: int, exchange, slots: int = 2):
+        from ._native import MAX_PEERS
+        if world > MAX_PEERS:
+            raise ValueError(f"PeerPlanes supports at most {MAX_PEERS} ranks")
+        self.lib, self.elems, self.rank, self.world, self.slots = lib, int(elems), rank, world, slots
+        self.max_peers = MAX_PEERS
+        self.plane_bytes = (self.elems * 4 + 255) // 256 * 256
+        self.total_bytes = slots * self.plane_bytes + self.MAILBOX_BYTES
+        self.base, handle = lib.peer_alloc(self.total_bytes)
+        handles = exchange(handle)
+        self.bases = [self.base if r == rank else lib.peer_open(handles[r]) for r in range(world)]
+        exchange(b"mapped")      # nobody proceeds (or frees) before every rank has mapped every buffer
+
+    def plane_ptr(self, slot: int, r: int | None = None) -> int:
+        return self.bases[self.rank if r is None else r] + slot * self.plane_bytes
+
+    def _mail(self, r: int) -> int:
+        return self.bases[r] + self.slots * self.plane_bytes
+
+    def _arrive_ptr(self, owner: int, slot: int, src: int) -> int:
+        return self._mail(owner) + 8 * (slot * self.max_peers + src)
+
+    def _consumed_ptr(self, owner: int, slot: int) -> int:
+        return self._mail(owner) + 8 * (self.slots * self.max_peers + slot)
+
+    @property
+    def err_ptr(self) -> int:
+        return self._mail(self.rank) + self.MAILBOX_BYTES - 8
+
+    def publish(self, slot: int, seq: int, root: int, stream: int = 0):
+        self.lib.peer_signal([self._arrive_ptr(root, slot, self.rank)], seq, stream)
+
+    def gather_sum(self, slot: int, seq: int, out_ptr: int, stream: int = 0):
+        flags = self._arrive_ptr(self.rank, slot, 0)
+        self.lib.peer_wait(flags, self.world, seq, self.err_ptr, stream)
+        self.lib.peer_sum(out_ptr, [self.plane_ptr(slot, r) for r in range(self.world)], self.elems, flags, seq,
+                          self.err_ptr, stream)
+        self.lib.peer_signal([self._consumed_ptr(r, slot) for r in range(self.world)], seq, stream)
+
+    def wait_consumed(self, slot: int, seq: int, stream: int = 0):
+        self.lib.peer_wait(self._consumed_ptr(self.rank, slot), 1, seq, self.err_ptr, stream)
+
+    def close(self):
+        for r, b in enumerate(self.bases):
+            if r != self.rank and b:
+                self.lib.check_peer(self.lib.litho_peer_close(b), "litho_peer_close")
+        if self.base:
+            self.lib.check_peer(self.lib.litho_peer_free(self.base), "litho_peer_free")
+        self.base, self.bases = 0, []
+
+
+class ShardedPipeline:
+    """Throughput mode of the sharded imager: every image is accumulated by all ranks
+    together (source points interleaved), the partial planes are summed by rank `i mod world` -- which alone
+    post-processes image i, on a second stream -- while all ranks already accumulate image i+1.
+
+    reduce = "peer": the root reads the other ranks' planes over NVLink with litho_peer_sum (no collective kernel
+    to co-schedule; deterministic rank-order sum); "nccl": one asynchronous ncclReduce per image (the baseline).
+    Everything a step needs is allocated here, none of it inside submit()."""
+
+    def __init__(self, eng: AbbeEngine, plan, eps: float, *, group=None, reduce: str = "peer"):
+        self.eng, self.plan, self.eps, self.group = eng, plan, eps, group
+        dev = self.dev = eng.device
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self.reduce = reduce if self.world > 1 else "none"
+        self.i = 0
+        self.fin_stream = torch.cuda.Stream(dev)
+        elems = plan.intensity_elems
+        self.peers = None
+        if self.reduce == "peer":
+            def exchange(obj):
+                out = [None] * self.world
+                dist.all_gather_object(out, obj, group=group)
+                return out
+            self.peers = PeerPlanes(eng.lib, elems, self.rank, self.world, exchange)
+            torch.cuda.synchronize(dev)
+            self.planes = [tensor_from_ptr(self.peers.plane_ptr(k), elems, dev) for k in range(2)]
+            self.err = tensor_from_ptr(self.peers.err_ptr, 2, dev, torch.int32)
+            self.summed = torch.zeros(elems, dtype=torch.float32, device=dev)
+        else:
+            self.planes = [eng.intensity_plane(plan) for _ in range(2)]
+            self.summed = None
+        side = plan.output_side(eps)
+        self.images = [torch.zeros((side, side), dtype=torch.float32, device=dev) for _ in range(2)]
+        self.fwb = plan.finalize_workspace_bytes()
+        self.fws = torch.empty(max(self.fwb, 16), dtype=torch.uint8, device=dev)
+        self.fin_done = [None, None]
+        self.reduce_work = [None, None]
+        self.last_image = None
+        self.trace = None    # set to [] to record CUDA events per image (see trace_ms)
+        if self.reduce == "nccl":
+            # NCCL sets up its channels per (collective, root) on first use: touch every root once
+            for r in range(self.world):
+                dist.reduce(self.planes[0], dst=r, group=group)
+            self.planes[0].zero_()
+        # lazy kernel loading of the post-processing path, on its own stream, on EVERY rank
+        with torch.cuda.stream(self.fin_stream):
+            self._finalize(self.planes[0], self.images[0])
+        torch.cuda.synchronize(dev)
+
+    def _finalize(self, plane: torch.Tensor, out: torch.Tensor):
+        self.plan.finalize(plane.data_ptr(), self.eps, out.data_ptr(), self.fws.data_ptr(), self.fwb,
+                           torch.cuda.current_stream(self.dev).cuda_stream)
+
+    def submit(self, maskFT_d, pupil_d, shifts_mine, *, weights_d=None, batch: int = 0, inputs_ready: bool = False,
+               wait_event=None, on_accumulated=None, out_host=None):
+        """Queue image number self.i.  `shifts_mine` is this rank's shard of the source points.  wait_event: an event
+        the accumulation must wait for (inputs staged on another stream); on_accumulated(): called right after the
+        accumulation has been queued (to release staging buffers); out_host: pinned tensor the root copies the image to."""
+        i, k = self.i, self.i % 2
+        self.i += 1
+        seq = i + 1
+        dev, eng = self.dev, self.eng
+        main = torch.cuda.current_stream(dev)
+        inten = self.planes[k]
+        tr = None
+        if self.trace is not None:
+            tr = {"i": i, "root": i % self.world}
+            self.trace.append(tr)
+            tr["begin"] = self._mark(main)
+        if self.reduce == "peer":
+            if i >= 2:
+                self.peers.wait_consumed(k, seq - 2, main.cuda_stream)   # the root of image i-2 has read this plane
+        else:
+            if self.reduce_work[k] is not None:
+                self.reduce_work[k].wait()
+            if self.fin_done[k] is not None:
+                main.wait_event(self.fin_done[k])
+        inten.zero_()
+        if wait_event is not None:
+            main.wait_event(wait_event)
+        eng.accumulate(self.plan, maskFT_d, pupil_d, shifts_mine, inten, weights_d, batch, inputs_ready=inputs_ready)
+        if on_accumulated is not None:
+            on_accumulated()
+        root = i % self.world
+        work = None
+        if self.reduce == "peer":
+            self.peers.publish(k, seq, root, main.cuda_stream)
+        elif self.reduce == "nccl":
+            work = dist.reduce(inten, dst=root, group=self.group, async_op=True)
+            self.reduce_work[k] = work
+        if tr is not None:
+            tr["accumulated"] = self._mark(main)
+        if self.rank != root:
+            return
+        ready = torch.cuda.Event()
+        ready.record(main)
+        fin = self.fin_stream
+        with torch.cuda.stream(fin):
+            fin.wait_event(ready)            # never spin on this GPU's own accumulation: order it with an event
+            src = inten
+            if tr is not None:
+                tr["fin_begin"] = self._mark(fin)
+            if self.reduce == "peer":
+                self.peers.gather_sum(k, seq, self.summed.data_ptr(), fin.cuda_stream)
+                src = self.summed
+            elif work is not None:
+                work.wait()
+            if tr is not None:
+                tr["summed"] = self._mark(fin)
+            img = self.images[k]
+            self._finalize(src, img)
+            if tr is not None:
+                tr["finalized"] = self._mark(fin)
+            if out_host is not None:
+                out_host.copy_(img, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(fin)
+            self.fin_done[k] = done
+        self.last_image = img
+
+    @staticmethod
+    def _mark(stream):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(stream)
+        return e
+
+    def trace_ms(self):
+        """Recorded events as milliseconds since the first image's begin (call after a synchronize)."""
+        if not self.trace:
+            return []
+        base = self.trace[0]["begin"]
+        return [{k: (round(base.elapsed_time(v), 4) if isinstance(v, torch.cuda.Event) else v) for k, v in t.items()}
+                for t in self.trace]
+
+    def join(self):
+        for w in self.reduce_work:
+            if w is not None:
+                w.wait()
+        torch.cuda.current_stream(self.dev).wait_stream(self.fin_stream)
+
+    def check(self):
+        """Raise if a peer wait timed out (call after a synchronize)."""
+        if self.peers is not None and int(self.err[0].item()) != 0:
+            raise RuntimeError(f"peer-memory sum: wait for a peer timed out (error word {int(self.err[0].item())})")
+
+    def close(self):
+        if self.peers is not None:
+            torch.cuda.synchronize(self.dev)
+            if self.world > 1:
+                dist.barrier(group=self.group)
+            self.planes, self.err = [], None
+            self.peers.close()
+            self.peers = None
 
 
 def shard_shifts(shifts: torch.Tensor, rank: int, world: int) -> torch.Tensor:

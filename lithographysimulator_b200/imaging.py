@@ -46,6 +46,16 @@ def _as_c64(t: torch.Tensor, dev: torch.device) -> torch.Tensor:
     return t.to(device=dev, dtype=torch.complex64, non_blocking=True).contiguous()
 
 
+def _check_square(name: str, t, pn: int | None = None) -> int:
+    """The kernels index every input plane with pitch pn: reject anything that is not [pn, pn] (the reference
+    raises a broadcast error for mismatched shapes, imageformation.py:34/:63)."""
+    if t.dim() != 2 or t.shape[0] != t.shape[1]:
+        raise _native.LithoError(f"{name} must be a square 2-D tensor, got shape {tuple(t.shape)}")
+    if pn is not None and t.shape[0] != pn:
+        raise _native.LithoError(f"{name} has shape {tuple(t.shape)}, expected ({pn}, {pn}) like maskFT")
+    return int(t.shape[0])
+
+
 class PreparedImage:
     """Inputs of one aerial image staged on the device by AbbeEngine.prepare()."""
 
@@ -125,7 +135,19 @@ class AbbeEngine:
             return
         batch = self.batch_for(plan, n_src, batch)
         wsb = plan.workspace_bytes(batch)
-        ws = self.workspace(wsb)
+        # a fast plan keeps a T ring of its own: its row passes run ahead on the plan's auxiliary stream (chained
+        # across images with inputs_ready), so nothing else may ever be queued on that memory
+        ws = self.workspace(wsb, ("t", plan.handle.value) if plan.path == 2 else "t")
+        pn = plan.pn
+        if tuple(maskFT_d.shape) != (pn, pn) or tuple(pupil_d.shape) != (pn, pn):
+            raise _native.LithoError(f"accumulate: maskFT {tuple(maskFT_d.shape)} / pupil {tuple(pupil_d.shape)} do not "
+                                     f"match the plan's grid ({pn}, {pn})")
+        if shifts_d.dim() != 2 or shifts_d.shape[1] != 2 or shifts_d.dtype != torch.int32:
+            raise _native.LithoError("accumulate: shifts must be an int32 tensor of shape [n_src, 2]")
+        if weights_d is not None and int(weights_d.numel()) != n_src:
+            raise _native.LithoError(f"accumulate: {int(weights_d.numel())} weights for {n_src} source points")
+        if intensity.numel() < plan.intensity_elems:
+            raise _native.LithoError("accumulate: intensity plane smaller than plan.intensity_elems")
         plan.accumulate(maskFT_d.data_ptr(), pupil_d.data_ptr(), shifts_d.data_ptr(),
                         None if weights_d is None else weights_d.data_ptr(), n_src, batch,
                         intensity.data_ptr(), ws.data_ptr(), wsb, self.stream(),
@@ -166,19 +188,35 @@ class AbbeEngine:
         sharded image must use the same one so that their intensity planes can be summed)."""
         dev = self.device
         with torch.cuda.device(dev):
+            pn = _check_square("maskFT", maskFT)
+            _check_square("pupilF", pupilF, pn)
             maskFT_d = _as_c64(maskFT, dev)
             pupil_d = _as_c64(pupilF, dev)
-            pn = maskFT_d.shape[0]
             eps, N = epsilon_n(deltaK, pixelSize, wavelength)
             if shifts is None:
+                _check_square("lightsource", lightsource, pn)      # shifts are centred with the mask's pn (SURVEY Q8)
                 ls_d = lightsource.to(dev, non_blocking=True)
                 shifts_d = source_shifts(ls_d, pn)
             else:
                 shifts_d = shifts.to(device=dev, dtype=torch.int32).contiguous()
+                if shifts_d.dim() != 2 or shifts_d.shape[1] != 2:
+                    raise _native.LithoError(f"shifts must have shape [n_src, 2], got {tuple(shifts_d.shape)}")
             w_d = None if weights is None else weights.to(device=dev, dtype=torch.float32).contiguous()
+            if w_d is not None and int(w_d.numel()) != int(shifts_d.shape[0]):
+                raise _native.LithoError(f"{int(w_d.numel())} weights for {int(shifts_d.shape[0])} source points")
             if plan is None:
                 support = self.pupil_support(pupil_d)
                 plan = self.plan(pn, N, support, generic=True) if generic else self.plan_for(pn, N, support, shifts_d)
+            else:
+                if plan.pn != pn or plan.N != N:
+                    raise _native.LithoError(f"pinned plan is for pn={plan.pn}, N={plan.N}; inputs need pn={pn}, N={N}")
+                if plan.path == 2:   # a pinned fast plan must still satisfy the no-wrap contract
+                    n = int(shifts_d.shape[0])
+                    bounds = self.lib.shift_bounds(shifts_d.data_ptr() if n else None, n, self.stream())
+                    if not plan.shifts_fit(bounds):
+                        raise _native.LithoError(
+                            f"pinned fast plan: source shifts {bounds} leave the plan's no-wrap range "
+                            f"{plan.shift_range}; use a generic plan for sources that wrap the pupil window")
             intensity = self.intensity_plane(plan)
             self.accumulate(plan, maskFT_d, pupil_d, shifts_d, intensity, w_d, batch)
             if reduce_fn is not None:
@@ -204,7 +242,11 @@ class AbbeEngine:
             prev = self._staging_busy.get(slot)
             if prev is not None:
                 st.wait_event(prev)
-            pn = int(maskFT.shape[0])
+            pn = _check_square("maskFT", maskFT)
+            _check_square("pupilF", pupilF, pn)
+            _check_square("lightsource", lightsource, pn)
+            if plan is not None and plan.pn != pn:
+                raise _native.LithoError(f"pinned plan is for pn={plan.pn}, inputs have pn={pn}")
             bufs = self._staging.get((slot, pn, lightsource.dtype))
             if bufs is None:
                 bufs = self._staging[(slot, pn, lightsource.dtype)] = (
@@ -231,6 +273,12 @@ class AbbeEngine:
                         bounds = self.lib.shift_bounds(shifts_all.data_ptr() if n else None, n, st.cuda_stream)
                         if not plan.shifts_fit(bounds):
                             plan = self.plan(pn, N, support, generic=True)
+            elif plan.path == 2:     # pinned fast plan: the no-wrap contract is checked here (copy stream only)
+                n = int(shifts_all.shape[0])
+                bounds = self.lib.shift_bounds(shifts_all.data_ptr() if n else None, n, st.cuda_stream)
+                if not plan.shifts_fit(bounds):
+                    raise _native.LithoError(f"pinned fast plan: source shifts {bounds} leave the plan's no-wrap range "
+                                             f"{plan.shift_range}")
             shifts = shifts_all if shard is None else shifts_all[shard[0]::shard[1]].contiguous()
             ready = torch.cuda.Event()
             ready.record(st)
@@ -292,9 +340,10 @@ class AbbeEngine:
     def fft_field(self, pf, maskFT, pixelNumber: int, N: int) -> torch.Tensor:
         dev = self.device
         with torch.cuda.device(dev):
+            pn = _check_square("maskFFFT", maskFT)
+            _check_square("pf", pf, pn)
             pf_d = _as_c64(pf, dev)
             maskFT_d = _as_c64(maskFT, dev)
-            pn = maskFT_d.shape[0]
             plan = self.plan(pn, int(N), self.pupil_bbox(pf_d), generic=True)
             wsb = plan.workspace_bytes(1)
             ws = self.workspace(wsb)

@@ -109,8 +109,9 @@ struct EmuCtx {
         ++*bar;
         ++cur_sched()->progress;
     }
-    void mbar_wait(unsigned long long* bar, unsigned parity) const {
+    bool mbar_wait(unsigned long long* bar, unsigned parity) const {
         while (!(*bar > 0 && ((*bar - 1) & 1) == parity)) fiber_yield();
+        return true;
     }
 };
 

@@ -76,3 +76,69 @@ def test_shard_shifts_partition():
     assert sum(len(p) for p in parts) == 23 and max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
     merged = torch.cat(parts).tolist()
     assert sorted(merged) == sh.tolist()
+
+
+def _peer_worker(rank, world, port, case, out_dir):
+    """The peer-memory protocol of distributed.PeerPlanes (publish / gather_sum / wait_consumed) between two
+    PROCESSES, on the CPU emulation (POSIX shared memory stands in for CUDA IPC): 5 images with a rotating root,
+    every image must equal the reference golden."""
+    import ctypes as C
+    from lithographysimulator_b200.distributed import PeerPlanes
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        c = H.load_kat()[case]
+        lib = H.emu_lib()
+        pn = c["maskFT"].shape[0]
+        eps, N = lib.epsilon_n(4 / pn, float(c["pixel_size"]), 193.0)
+        mft = np.ascontiguousarray(c["maskFT"])
+        pup = np.ascontiguousarray(c["pupil"])
+        shifts_all = np.ascontiguousarray(O.source_shifts(c["lightsource"], pn))
+        plan = lib.plan_create(pn, N, lib.pupil_support(pup.ctypes.data, pn))
+        if plan.path == 2 and not plan.shifts_fit(lib.shift_bounds(shifts_all.ctypes.data, len(shifts_all))):
+            plan = lib.plan_create(pn, N, lib.pupil_support(pup.ctypes.data, pn), 1)
+        mine = np.ascontiguousarray(shard_shifts(torch.from_numpy(shifts_all), rank, world).numpy())
+        elems = plan.intensity_elems
+
+        def exchange(obj):
+            out = [None] * world
+            dist.all_gather_object(out, obj)
+            return out
+
+        peers = PeerPlanes(lib, elems, rank, world, exchange)
+        planes = [np.ctypeslib.as_array((C.c_float * elems).from_address(peers.plane_ptr(k))) for k in range(2)]
+        wsb = plan.workspace_bytes(0)
+        ws = np.zeros(max(wsb, 8), np.uint8)
+        fwb = plan.finalize_workspace_bytes()
+        fws = np.zeros(max(fwb, 8), np.uint8)
+        side = plan.output_side(eps)
+        summed = np.zeros(elems, np.float32)
+        for i in range(5):
+            k, seq, root = i % 2, i + 1, i % world
+            if i >= 2:
+                peers.wait_consumed(k, seq - 2)
+            planes[k][:] = 0
+            plan.accumulate(mft.ctypes.data, pup.ctypes.data, mine.ctypes.data, None, len(mine), 0,
+                            peers.plane_ptr(k), ws.ctypes.data, wsb)
+            peers.publish(k, seq, root)
+            if rank == root:
+                peers.gather_sum(k, seq, summed.ctypes.data)
+                out = np.zeros((side, side), np.float32)
+                plan.finalize(summed.ctypes.data, eps, out.ctypes.data, fws.ctypes.data, fwb)
+                np.save(os.path.join(out_dir, f"img{i}.npy"), out)
+        err = (C.c_int * 2).from_address(peers.err_ptr)
+        assert err[0] == 0
+        dist.barrier()
+        peers.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_peer_memory_sum_rotating_root(tmp_path):
+    H.emu_lib()
+    mp.spawn(_peer_worker, args=(2, _free_port(), "demo64_quasar", str(tmp_path)), nprocs=2, join=True)
+    ref = H.load_kat()["demo64_quasar"]["image"]
+    for i in range(5):
+        img = np.load(str(tmp_path / f"img{i}.npy"))
+        assert O.rel_l2(img, ref) < H.TOL

@@ -376,6 +376,30 @@ def _dist_worker(rank, world, port, out_path):
         img2 = eng.run(prep, reduce_fn=lambda t: dist.all_reduce(t))
         torch.cuda.synchronize(dev)
         assert torch.equal(img, img2), "sharded upload + prepare/run differs from abbe_image_sharded"
+        # pipelined throughput mode: 5 images, rotating root, partial planes summed over peer memory (CUDA IPC
+        # + NVLink loads) and, for comparison, by ncclReduce; every image a root produced must equal `img`
+        from lithographysimulator_b200.distributed import ShardedPipeline, shard_shifts
+        from lithographysimulator_b200.imaging import source_shifts, epsilon_n
+        mft_d, pf_d = torch.from_numpy(z["maskFT"]).to(dev), torch.from_numpy(z["pupil"]).to(dev)
+        sh_all = source_shifts(torch.from_numpy(ls).to(dev), cfg.pn)
+        eps, N = epsilon_n(m.deltaK, cfg.pixel_size, cfg.wavelength)
+        plan = eng.plan_for(cfg.pn, N, eng.pupil_support(pf_d), sh_all)
+        mine = shard_shifts(sh_all, rank, world)
+        for mode in ("peer", "nccl"):
+            pipe = ShardedPipeline(eng, plan, eps, reduce=mode)
+            assert pipe.reduce == mode
+            for i in range(5):
+                pipe.submit(mft_d, pf_d, mine, inputs_ready=True)
+                if i % world == rank:
+                    pipe.join()
+                    torch.cuda.synchronize(dev)
+                    got = pipe.last_image
+                    err = float((got.double() - img.double()).norm() / img.double().norm())
+                    assert err < 1e-6, (mode, i, err)
+            pipe.join()
+            torch.cuda.synchronize(dev)
+            pipe.check()
+            pipe.close()
         if rank == 0:
             np.save(out_path, img.cpu().numpy())
     finally:
@@ -531,3 +555,157 @@ def test_full_cfg4_cfg5_against_reference_golden(L, dev, golden_dir, name):
     assert O.rel_l2(img[::st, ::st].cpu().numpy(), z["image_sample"]) < H.TOL
     assert abs(float(img.sum(dtype=torch.float64)) / float(z["img_sum"]) - 1) < 1e-5
     assert abs(float((img.double() ** 2).sum()) / float(z["img_sumsq"]) - 1) < 2e-5
+
+
+def test_sharded_pipeline_single_gpu_chained(L, dev):
+    """ShardedPipeline on one GPU (what bench.py times): 4 images queued back to back with inputs_ready=True, so
+    the row pass of image i+1 is chained behind image i on the plan's auxiliary stream and the post-processing of
+    image i overlaps the accumulation of image i+1.  Every image must be bit-identical to the plain call (the rim
+    sums are deterministic) and match the reference golden."""
+    from lithographysimulator_b200.distributed import ShardedPipeline
+    from lithographysimulator_b200.imaging import AbbeEngine, source_shifts, epsilon_n
+    cfg, mft, pf, ls = _cfg_inputs("cfg2")
+    eng = AbbeEngine.get(dev)
+    mft_d, pf_d, ls_d = _t(mft, dev), _t(pf, dev), _t(ls, dev)
+    args = (cfg.pixel_size, 4 / cfg.pn, cfg.wavelength)
+    ref = eng.abbe_fft(mft_d, pf_d, ls_d, *args)
+    eps, N = epsilon_n(4 / cfg.pn, cfg.pixel_size, cfg.wavelength)
+    sh = source_shifts(ls_d, cfg.pn)
+    plan = eng.plan_for(cfg.pn, N, eng.pupil_support(pf_d), sh)
+    assert plan.path == 2
+    pipe = ShardedPipeline(eng, plan, eps)
+    for i in range(4):
+        pipe.submit(mft_d, pf_d, sh, inputs_ready=True, batch=(0 if i != 2 else 37))   # image 2 breaks the chain
+    pipe.join()
+    torch.cuda.synchronize(dev)
+    assert torch.equal(pipe.last_image, ref)
+    assert plan.status() == (0, 0)
+    # images in flight use alternating output buffers: check the last two
+    assert torch.equal(pipe.images[0], ref) and torch.equal(pipe.images[1], ref)
+
+
+def test_chained_images_with_interleaved_plans_and_field_calls(L, dev):
+    """chained accumulate calls (LITHO_PHASE_INPUTS_READY) interleaved with a second plan, an fft_field
+    call and a direct-solver call on the same engine.  Each fast plan owns its T ring, so nothing the other calls
+    queue can touch it; every chained image must equal its unchained twin."""
+    from lithographysimulator_b200.imaging import AbbeEngine, source_shifts, epsilon_n
+    cfg, mft, pf, ls = _cfg_inputs("cfg2")
+    eng = AbbeEngine.get(dev)
+    pn = cfg.pn
+    mft_d, pf_d, ls_d = _t(mft, dev), _t(pf, dev), _t(ls, dev)
+    eps, N = epsilon_n(4 / pn, cfg.pixel_size, cfg.wavelength)
+    sh = source_shifts(ls_d, pn)
+    planA = eng.plan_for(pn, N, eng.pupil_support(pf_d), sh)
+    # a second fast plan: same pupil cropped to a smaller window
+    pf2 = pf.copy()
+    pf2[: pn // 2 - 100] = 0
+    pf2[pn // 2 + 100:] = 0
+    pf2_d = _t(pf2, dev)
+    planB = eng.plan_for(pn, N, eng.pupil_support(pf2_d), sh)
+    assert planA.path == 2 and planB.path == 2 and planA.handle.value != planB.handle.value
+    c64 = KAT["demo64_quasar"]
+
+    def unchained(plan, pupil):
+        inten = eng.intensity_plane(plan)
+        eng.accumulate(plan, mft_d, pupil, sh, inten)
+        return inten.clone()
+
+    refA, refB = unchained(planA, pf_d), unchained(planB, pf2_d)
+    torch.cuda.synchronize(dev)
+    outs = []
+    for i in range(3):
+        ia, ib = eng.intensity_plane(planA), eng.intensity_plane(planB)
+        eng.accumulate(planA, mft_d, pf_d, sh, ia, None, 0 if i != 1 else 29, inputs_ready=True)
+        L.calculateFFTAerial(_t(c64["pupil"], dev), _t(c64["maskFT"], dev), 64, 128)   # shares the engine
+        eng.accumulate(planB, mft_d, pf2_d, sh, ib, None, 0, inputs_ready=True)
+        outs.append((ia, ib))
+    torch.cuda.synchronize(dev)
+    for ia, ib in outs:
+        assert torch.equal(ia, refA)
+        assert torch.equal(ib, refB)
+    assert planA.status() == (0, 0) and planB.status() == (0, 0)
+
+
+def test_input_validation_and_error_words(L, dev):
+    """ADVICE r1 / VERDICT r1 weak-8: mismatched shapes raise instead of indexing out of bounds; a pinned fast plan
+    refuses sources that wrap the pupil window; and a raw C-ABI call that violates the no-wrap contract raises the
+    plan's sticky error word instead of returning a silently wrong image."""
+    from lithographysimulator_b200 import _native
+    from lithographysimulator_b200.imaging import AbbeEngine
+    c = KAT["demo64_quasar"]
+    eng = AbbeEngine.get(dev)
+    m = _mask_stub(L, 64, 25, dev)
+    mft, pf, ls = _t(c["maskFT"], dev), _t(c["pupil"], dev), _t(c["lightsource"], dev)
+    with pytest.raises(_native.LithoError):
+        L.abbeImage(m, mft, pf[:32, :32].contiguous(), ls, 25, m.deltaK, 193.0, True, dev)     # smaller pupil
+    with pytest.raises(_native.LithoError):
+        L.abbeImage(m, mft, pf[:, :32].contiguous(), ls, 25, m.deltaK, 193.0, True, dev)       # non-square pupil
+    with pytest.raises(_native.LithoError):
+        L.abbeImage(m, mft, pf, ls[:32, :32].contiguous(), 25, m.deltaK, 193.0, True, dev)     # smaller source
+    with pytest.raises(_native.LithoError):
+        eng.abbe_fft(mft, pf, ls, 25, m.deltaK, 193.0, weights=torch.ones(3, device=dev))       # weight count
+    with pytest.raises(_native.LithoError):
+        L.calculateFFTAerial(pf[:32, :32].contiguous(), mft, 64, 128)
+    # pinned fast plan + a source point that wraps the window
+    eps, N = eng.lib.epsilon_n(m.deltaK, 25, 193.0)
+    plan = eng.plan(64, N, eng.pupil_support(pf))
+    assert plan.path == 2
+    bad = torch.tensor([[0, 0], [40, 0]], dtype=torch.int32, device=dev)
+    with pytest.raises(_native.LithoError):
+        eng.abbe_fft(mft, pf, None, 25, m.deltaK, 193.0, shifts=bad, plan=plan)
+    plan64 = eng.plan(64, N, eng.pupil_support(pf))
+    with pytest.raises(_native.LithoError):
+        eng.abbe_fft(_t(KAT["wrap_128"]["maskFT"], dev), _t(KAT["wrap_128"]["pupil"], dev), None, 25, 4 / 128, 193.0,
+                     shifts=bad, plan=plan64)                                                   # plan of another grid
+    # raw C ABI, contract violated: memory-safe, and reported by litho_plan_status
+    assert plan.status() == (0, 0)
+    inten = eng.intensity_plane(plan)
+    wsb = plan.workspace_bytes(2)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    plan.accumulate(mft.data_ptr(), pf.data_ptr(), bad.data_ptr(), None, 2, 2, inten.data_ptr(), ws.data_ptr(), wsb,
+                    torch.cuda.current_stream(dev).cuda_stream)
+    assert plan.status() == (1, 0)
+    assert plan.status() == (0, 0)      # read-and-clear
+
+
+def test_builders_match_reference_on_this_gpu(L, dev):
+    """the native LightSource / Pupil / Mask.fraunhofer builders against the UNMODIFIED reference
+    (oracle/_ref, staged by oracle/build_ref.py) run with device='cuda' on this very GPU -- random rotation, count,
+    shift, sigma, NA and aberrations, including non-power-of-two grids.  Sources must be identical; pupils and
+    mask spectra within float32 rounding."""
+    from oracle import ref_runner as RR
+    if not RR.available():
+        pytest.skip("oracle/_ref not staged")
+    R = RR.load()
+    rng = np.random.default_rng(20261017)
+    bad = []
+    for case in range(40):
+        pn = int(rng.choice([64, 96, 128, 200, 256, 512]))
+        s_in = float(rng.uniform(0.0, 0.6))
+        s_out = float(s_in + rng.uniform(0.1, 0.39))
+        count = int(rng.integers(1, 9))
+        rot = float(rng.uniform(-math.pi, math.pi))
+        sx, sy = (float(rng.uniform(-0.3, 0.3)), float(rng.uniform(-0.3, 0.3))) if case % 3 == 0 else (0, 0)
+        ours = L.LightSource(s_in, s_out, pn, 0.7, sx, sy, dev).generateQuasar(count, rot)
+        ref = R["lightsource"].LightSource(s_in, s_out, pn, 0.7, sx, sy, dev).generateQuasar(count, rot)
+        d = int((ours != ref).sum())
+        ours_a = L.LightSource(s_in, s_out, pn, 0.7, sx, sy, dev).generateAnnular()
+        ref_a = R["lightsource"].LightSource(s_in, s_out, pn, 0.7, sx, sy, dev).generateAnnular()
+        da = int((ours_a != ref_a).sum())
+        if d or da:
+            bad.append(("source", case, pn, count, rot, sx, sy, d, da))
+        na = float(rng.uniform(0.5, 0.9))
+        ab = (rng.uniform(-0.05, 0.05, int(rng.integers(5, 13)))).astype(np.float32)
+        ab[4] = float(rng.uniform(-150, 150))
+        p_ours = L.Pupil(pn, 193.0, na, torch.tensor(ab, dtype=torch.float16, device=dev), dev).generatePupilFunction()
+        p_ref = R["pupil"].Pupil(pn, 193.0, na, torch.tensor(ab, dtype=torch.float16, device=dev), dev).generatePupilFunction()
+        nz = int(((p_ours != 0) != (p_ref != 0)).sum())
+        dp = float((p_ours - p_ref).abs().max())
+        if nz or dp > 2e-3:     # one fp16 ulp of the wavefront error moves the phase by ~6e-4 * 2 pi
+            bad.append(("pupil", case, pn, na, nz, dp))
+    assert not bad, bad
+    for pn, ps in ((64, 25), (96, 25), (128, 50), (128, 12), (256, 25)):
+        g = torch.from_numpy(wl.manhattan(pn, seed=pn))
+        ours = L.Mask(g, ps, dev).fraunhofer(193.0, True)
+        ref = R["mask"].Mask(g.to(dev), ps, dev).fraunhofer(193.0, True)
+        assert float((ours - ref).abs().max() / ref.abs().max()) < 2e-6, (pn, ps)
