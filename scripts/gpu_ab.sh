@@ -1,25 +1,19 @@
 #!/bin/bash
-# A/B runs of the headline bench under environment toggles (no ncu).  Usage: scripts/gpu_ab.sh TAG "ENV1=.. ENV2=..|--flags" ...
-# Each argument after TAG is "<env assignments>|<bench flags>"; prints one summary line per run.
-TAG=${1:-ab}; shift
+# A/B on ONE box: the previous build (.ab_old/, git-ignored copy of an older commit with its own .so) against the
+# working tree, alternating, same bench command.  Usage: gpurun -- 'bash scripts/gpu_ab.sh tag'
+TAG=${1:-ab}
 mkdir -p gpurun_out
-i=0
-for spec in "$@"; do
-  envs="${spec%%|*}"; flags="${spec#*|}"
-  [ "$flags" == "$spec" ] && flags=""
-  i=$((i+1))
-  log=gpurun_out/${TAG}_$i.log
-  env $envs timeout 400 python bench.py --steps ${STEPS:-8} --warmup 4 --no-cpu-baseline $flags > $log 2>&1
-  python - "$log" "$spec" <<'PY'
-import json, sys
-log, spec = sys.argv[1], sys.argv[2]
+for rep in 1 2; do
+  (cd .ab_old && timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline) > gpurun_out/${TAG}_old_$rep.log 2>&1
+  timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-library-baseline --trace > gpurun_out/${TAG}_new_$rep.log 2>&1
+done
+for f in gpurun_out/${TAG}_old_1.log gpurun_out/${TAG}_new_1.log gpurun_out/${TAG}_old_2.log gpurun_out/${TAG}_new_2.log; do
+  echo "== $f"; tail -1 $f | python -c "
+import sys, json
 try:
-    d = json.loads(open(log).read().strip().splitlines()[-1])
-    r = d["roofline"]
-    print("%-40s %.2f img/s %.3f ms  e2e %.2f (chk %s) cols %.1f us rows %.1f us frac %.3f step-frac %.3f" % (
-        spec, d["value"], d["ms_per_step"], d["e2e"]["value"], d["e2e"].get("rel_l2_vs_resident_path"),
-        r["ms_per_launch"] * 1e3, r["rows_kernel"]["ms_per_launch"] * 1e3, r["frac"], r["whole_step"]["frac"]))
+    d = json.loads(sys.stdin.read())
+    print({k: d.get(k) for k in ('value', 'ms_per_step')}, d['e2e']['value'], d['breakdown_ms'], d['roofline']['ms_per_launch'], d['roofline']['rows_kernel']['ms_per_launch'], d.get('trace'))
 except Exception as e:
-    print(spec, "FAILED", e); print(open(log).read()[-1500:])
-PY
+    print('unparsed', e)
+"
 done

@@ -671,8 +671,9 @@ def test_input_validation_and_error_words(L, dev):
 def test_builders_match_reference_on_this_gpu(L, dev):
     """the native LightSource / Pupil / Mask.fraunhofer builders against the UNMODIFIED reference
     (oracle/_ref, staged by oracle/build_ref.py) run with device='cuda' on this very GPU -- random rotation, count,
-    shift, sigma, NA and aberrations, including non-power-of-two grids.  Sources must be identical; pupils and
-    mask spectra within float32 rounding."""
+    shift, sigma, NA and aberrations, including non-power-of-two grids.  Sources and pupil supports must be
+    identical, mask spectra within float32 rounding, pupil phases within two fp16 ulps of the wavefront error on at
+    most a few percent of the pixels (CPU-vs-CUDA ATen rounding of r**3, see below)."""
     from oracle import ref_runner as RR
     if not RR.available():
         pytest.skip("oracle/_ref not staged")
@@ -701,8 +702,12 @@ def test_builders_match_reference_on_this_gpu(L, dev):
         p_ref = R["pupil"].Pupil(pn, 193.0, na, torch.tensor(ab, dtype=torch.float16, device=dev), dev).generatePupilFunction()
         nz = int(((p_ours != 0) != (p_ref != 0)).sum())
         dp = float((p_ours - p_ref).abs().max())
-        if nz or dp > 2e-3:     # one fp16 ulp of the wavefront error moves the phase by ~6e-4 * 2 pi
-            bad.append(("pupil", case, pn, na, nz, dp))
+        frac = float(((p_ours - p_ref).abs() > 1e-6).sum()) / (pn * pn)
+        # Support identical.  Values: the native replay models the reference's CPU tensors (the goldens are CPU
+        # runs); CUDA ATen rounds r**3 twice where CPU ATen rounds once, which moves the fp16 wavefront error of a
+        # few pixels by one or two ulps (2^-11 .. 2^-10 waves = 3.1e-3 .. 6.2e-3 rad) -- nothing larger may appear.
+        if nz or dp > 2 * math.pi * 2 ** -9 or frac > 0.05:
+            bad.append(("pupil", case, pn, na, nz, dp, frac))
     assert not bad, bad
     for pn, ps in ((64, 25), (96, 25), (128, 50), (128, 12), (256, 25)):
         g = torch.from_numpy(wl.manhattan(pn, seed=pn))
