@@ -104,14 +104,21 @@ class ShardedPipeline:
     to co-schedule; deterministic rank-order sum); "nccl": one asynchronous ncclReduce per image (the baseline).
     Everything a step needs is allocated here, none of it inside submit()."""
 
-    def __init__(self, eng: AbbeEngine, plan, eps: float, *, group=None, reduce: str = "peer"):
+    def __init__(self, eng: AbbeEngine, plan, eps: float, *, group=None, reduce: str = "peer", slots: int | None = None,
+                 fin_priority: int | None = None):
+        import os
         self.eng, self.plan, self.eps, self.group = eng, plan, eps, group
+        # plane slots: an image's plane is reused `slots` images later, after its root has read it
+        self.slots = int(os.environ.get("LITHO_PLANE_SLOTS", "3")) if slots is None else slots
+        # the summing / post-processing stream outranks the accumulation: its few CTAs take the next free SM slots
+        # instead of queueing behind the second wave of a column pass, so planes are released early
+        prio = int(os.environ.get("LITHO_FIN_PRIORITY", "-1")) if fin_priority is None else fin_priority
         dev = self.dev = eng.device
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if self.world > 1 else 0
         self.reduce = reduce if self.world > 1 else "none"
         self.i = 0
-        self.fin_stream = torch.cuda.Stream(dev)
+        self.fin_stream = torch.cuda.Stream(dev, priority=prio)
         elems = plan.intensity_elems
         self.peers = None
         if self.reduce == "peer":
@@ -119,20 +126,20 @@ class ShardedPipeline:
                 out = [None] * self.world
                 dist.all_gather_object(out, obj, group=group)
                 return out
-            self.peers = PeerPlanes(eng.lib, elems, self.rank, self.world, exchange)
+            self.peers = PeerPlanes(eng.lib, elems, self.rank, self.world, exchange, slots=self.slots)
             torch.cuda.synchronize(dev)
-            self.planes = [tensor_from_ptr(self.peers.plane_ptr(k), elems, dev) for k in range(2)]
+            self.planes = [tensor_from_ptr(self.peers.plane_ptr(k), elems, dev) for k in range(self.slots)]
             self.err = tensor_from_ptr(self.peers.err_ptr, 2, dev, torch.int32)
             self.summed = torch.zeros(elems, dtype=torch.float32, device=dev)
         else:
-            self.planes = [eng.intensity_plane(plan) for _ in range(2)]
+            self.planes = [eng.intensity_plane(plan) for _ in range(self.slots)]
             self.summed = None
         side = plan.output_side(eps)
         self.images = [torch.zeros((side, side), dtype=torch.float32, device=dev) for _ in range(2)]
         self.fwb = plan.finalize_workspace_bytes()
         self.fws = torch.empty(max(self.fwb, 16), dtype=torch.uint8, device=dev)
-        self.fin_done = [None, None]
-        self.reduce_work = [None, None]
+        self.fin_done = [None] * self.slots
+        self.reduce_work = [None] * self.slots
         self.last_image = None
         self.trace = None    # set to [] to record CUDA events per image (see trace_ms)
         if self.reduce == "nccl":
@@ -154,7 +161,7 @@ class ShardedPipeline:
         """Queue image number self.i.  `shifts_mine` is this rank's shard of the source points.  wait_event: an event
         the accumulation must wait for (inputs staged on another stream); on_accumulated(): called right after the
         accumulation has been queued (to release staging buffers); out_host: pinned tensor the root copies the image to."""
-        i, k = self.i, self.i % 2
+        i, k = self.i, self.i % self.slots
         self.i += 1
         seq = i + 1
         dev, eng = self.dev, self.eng
@@ -166,8 +173,8 @@ class ShardedPipeline:
             self.trace.append(tr)
             tr["begin"] = self._mark(main)
         if self.reduce == "peer":
-            if i >= 2:
-                self.peers.wait_consumed(k, seq - 2, main.cuda_stream)   # the root of image i-2 has read this plane
+            if i >= self.slots:   # the root of the image that last used this plane has read it
+                self.peers.wait_consumed(k, seq - self.slots, main.cuda_stream)
         else:
             if self.reduce_work[k] is not None:
                 self.reduce_work[k].wait()
@@ -205,7 +212,7 @@ class ShardedPipeline:
                 work.wait()
             if tr is not None:
                 tr["summed"] = self._mark(fin)
-            img = self.images[k]
+            img = self.images[(i // self.world) % 2]     # this rank's turns as root alternate between two buffers
             self._finalize(src, img)
             if tr is not None:
                 tr["finalized"] = self._mark(fin)
