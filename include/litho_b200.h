@@ -126,6 +126,23 @@ int litho_abbe_fft_accumulate_ex(const litho_plan_t* plan, const void* maskFT, c
                                  float* intensity, void* workspace, size_t workspace_bytes, void* stream,
                                  int phases);
 
+/* Focus batching (BASELINE cfg5: one mask, one source, 16 defocus values): the hot loop of abbeImage for
+ * n_focus pupil functions at once -- what the reference does with n_focus calls of abbeImage (imageformation.py:47-77)
+ * on pupils from Pupil.generatePupilFunction (pupil.py:32-35, defocus in aberrations[4], pupil.py:88-100).
+ *   pupils:      n_focus planes of pn x pn complex64, pupil_stride ELEMENTS apart; every pupil's support must lie in
+ *                the plan's window and share its rim extents (true for focus/aberration variants of one pupil:
+ *                |P| = 1 on the same disc)
+ *   intensities: n_focus planes of plan.intensity_elems floats, intensity_stride ELEMENTS apart, accumulated into
+ * One row pass serves all focus values: the work items of a (source point, window row) are adjacent for every focus
+ * value, so the shifted mask-spectrum row crosses HBM/L2 once and is multiplied by n_focus pupil rows; then one column
+ * pass per focus value.  Generic plans fall back to one focus value at a time.  batch <= 0: plan default / n_focus.
+ * Results are bit-identical to n_focus separate litho_abbe_fft_accumulate calls. */
+size_t litho_plan_workspace_bytes_focus(const litho_plan_t* plan, int batch, int n_focus);
+int litho_abbe_fft_accumulate_focus(const litho_plan_t* plan, const void* maskFT, const void* pupils, int n_focus,
+                                    size_t pupil_stride, const int32_t* shifts, const float* weights, int n_src,
+                                    int batch, float* intensities, size_t intensity_stride, void* workspace,
+                                    size_t workspace_bytes, void* stream);
+
 /* Post-processing of abbeImage(fft=True)                      imageformation.py:69-75
  * abs -> bilinear resample by 1/eps -> zero border; out has litho_fft_output_side(pn,eps)^2 floats. */
 int litho_fft_output_side(int pn, double eps);

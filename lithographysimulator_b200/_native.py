@@ -51,6 +51,9 @@ SYMBOLS = [
     ("litho_plan_status", C.c_int, [_P, C.POINTER(C.c_int), _P]),
     ("litho_abbe_fft_accumulate", C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P, C.c_size_t, _P]),
     ("litho_abbe_fft_accumulate_ex", C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P, C.c_size_t, _P, C.c_int]),
+    ("litho_plan_workspace_bytes_focus", C.c_size_t, [_P, C.c_int, C.c_int]),
+    ("litho_abbe_fft_accumulate_focus", C.c_int, [_P, _P, _P, C.c_int, C.c_size_t, _P, _P, C.c_int, C.c_int, _P, C.c_size_t,
+                                                  _P, C.c_size_t, _P]),
     ("litho_mask_spectrum_workspace_bytes", C.c_size_t, [C.c_int, C.c_double, C.c_int]),
     ("litho_mask_spectrum", C.c_int, [_P, C.c_int, C.c_double, C.c_int, _P, _P, C.c_size_t, _P]),
     ("litho_direct_operator", C.c_int, [C.c_int, C.c_double, C.c_double, C.c_int, _P, _P]),
@@ -189,6 +192,16 @@ class Plan:
         self.lib.check(self.lib.litho_abbe_fft_accumulate_ex(self.handle, maskFT, pupil, shifts, weights, n_src, batch,
                                                              intensity, workspace, workspace_bytes, stream, phases),
                        "litho_abbe_fft_accumulate")
+
+    def workspace_bytes_focus(self, batch: int, n_focus: int) -> int:
+        return int(self.lib.litho_plan_workspace_bytes_focus(self.handle, batch, n_focus))
+
+    def accumulate_focus(self, maskFT, pupils, n_focus, pupil_stride, shifts, weights, n_src, batch, intensities,
+                         intensity_stride, workspace, workspace_bytes, stream=0):
+        self.lib.check(self.lib.litho_abbe_fft_accumulate_focus(self.handle, maskFT, pupils, n_focus, pupil_stride, shifts,
+                                                                weights, n_src, batch, intensities, intensity_stride,
+                                                                workspace, workspace_bytes, stream),
+                       "litho_abbe_fft_accumulate_focus")
 
     def status(self, stream=0):
         """(shift_clamped, tile_copy_lost) sticky error words of a fast plan, read and cleared (synchronises)."""

@@ -114,8 +114,14 @@ struct FastRowsParams {
     const int2_* shifts;
     int s_begin, batch;
     const cplx* tables;
-    cplx* T;  // [batch][2][Sr][M]
+    cplx* T;  // [n_focus][batch][2][Sr][M]
     int* status;  // plan-owned device words: [0] set to 1 when a shift had to be clamped (contract violated)
+    // focus batching (BASELINE cfg5): n_focus pupil planes (pupil + f*pupil_stride) share the mask
+    // spectrum and the source points; work items of one (source point, window row) are adjacent for all focus
+    // values and both residues, so the mask row is fetched from L2/HBM once and served by L1 to the others
+    int n_focus;            // >= 1
+    size_t pupil_stride;    // elements between consecutive pupil planes
+    size_t t_focus_stride;  // elements between the T blocks of consecutive focus values (batch_alloc*2*Sr*M)
 };
 
 struct FastColsParams {
@@ -157,12 +163,13 @@ LITHO_HD void fast_tables_wait(const Ctx& ctx) {
 // the rim input folded onto slot 0.  Branch-free loads (index clamped, value masked afterwards) so that all
 // loads of a half are in flight together instead of one load-use round trip per element.
 template <int M, int PPT>
-LITHO_HD void fast_row_load(cplx (&v)[PPT], const FastRowsParams& P, int s, int line, int r, int g, const cplx* tab) {
+LITHO_HD void fast_row_load(cplx (&v)[PPT], const FastRowsParams& P, int s, int line, int r, int g, const cplx* tab,
+                            int f = 0) {
     using F = FastShape<M, PPT>;
     constexpr int TG = F::TG;
     constexpr int H = PPT / 2;
     const int2_ sh = P.shifts[s];
-    const cplx* prow = P.pupil + (size_t)(P.pr0 + line) * P.pn + P.pc0;
+    const cplx* prow = P.pupil + (size_t)f * P.pupil_stride + (size_t)(P.pr0 + line) * P.pn + P.pc0;
     // shifts are inside the plan's no-wrap range by contract; clamping keeps a violated contract
     // memory-safe (the result is then wrong, never out of bounds)
     const int mr = iclamp(P.pr0 + line + sh.x, 0, P.pn - 1);
@@ -277,7 +284,8 @@ LITHO_HD void fast_rows_body(const FastRowsParams& P, const Ctx& ctx, cplx* smem
     const int grp = ctx.tid() / TG;
     const int g = ctx.tid() - grp * TG;
     cplx* ex = smem + F::NTAB_PAD + grp * Sh::SMEM_ELEMS;
-    const int total = P.batch * P.Sr * 2;
+    const int nf = P.n_focus > 1 ? P.n_focus : 1;
+    const int total = P.batch * P.Sr * 2 * nf;
     const int stride = ctx.gdx() * F::ROW_GROUPS;
     const int rounds = (total + stride - 1) / stride;
     const SmemTw<M, PPT> tw{tab};
@@ -286,20 +294,27 @@ LITHO_HD void fast_rows_body(const FastRowsParams& P, const Ctx& ctx, cplx* smem
     for (int it = 0; it < rounds; ++it) {
         const int item = it * stride + ctx.bx() * F::ROW_GROUPS + grp;
         const bool active = item < total;
+        // item = ((sl*Sr + line)*nf + f)*2 + r : residue fastest, then focus value, then window row, then source point
         const int r = item & 1;
-        const int li = item >> 1;
+        int li = item >> 1;
+        int f = 0;
+        if (nf > 1) {
+            const int q = li / nf;
+            f = active ? li - q * nf : 0;
+            li = q;
+        }
         const int sl = active ? li / P.Sr : 0;
         const int line = active ? li - sl * P.Sr : 0;
         cplx v[PPT];
         if (active) {
-            fast_row_load<M, PPT>(v, P, P.s_begin + sl, line, r, g, tab);
+            fast_row_load<M, PPT>(v, P, P.s_begin + sl, line, r, g, tab, f);
         } else {
 #pragma unroll
             for (int e = 0; e < PPT; ++e) v[e] = mk(0.f, 0.f);
         }
         fft_run<M, PPT, false>(v, ex, 1, g, tw, gs);
         if (active) {
-            cplx* dst = P.T + ((size_t)(sl * 2 + r) * P.Sr + line) * M + g;
+            cplx* dst = P.T + (size_t)f * P.t_focus_stride + ((size_t)(sl * 2 + r) * P.Sr + line) * M + g;
 #pragma unroll
             for (int e = 0; e < PPT; ++e) dst[TG * e] = v[e];
         }

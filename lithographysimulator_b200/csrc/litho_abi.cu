@@ -916,16 +916,25 @@ static size_t generic_t_bytes(const litho_plan* p, int batch) {
     return (size_t)batch * p->zp.R * p->Sr * p->zp.Wr * sizeof(cplx);
 }
 
-size_t litho_plan_workspace_bytes(const litho_plan_t* p, int batch) {
-    if (!p) return 0;
-    if (batch <= 0) batch = p->default_batch;
+// default source points per launch pair when n_focus pupils are batched: the T ring holds n_focus blocks per point
+static int default_batch_focus(const litho_plan* p, int n_focus) {
+    if (n_focus <= 1) return p->default_batch;
+    int b = p->default_batch / n_focus;
+    return b < 1 ? 1 : b;
+}
+
+size_t litho_plan_workspace_bytes_focus(const litho_plan_t* p, int batch, int n_focus) {
+    if (!p || n_focus < 1) return 0;
+    if (batch <= 0) batch = default_batch_focus(p, n_focus);
     if (p->path == 2) {
-        const size_t fast = (size_t)LITHO_TSLOTS * batch * 2 * p->Sr * p->Mf * sizeof(cplx);  // T slots (ring)
+        const size_t fast = (size_t)LITHO_TSLOTS * batch * n_focus * 2 * p->Sr * p->Mf * sizeof(cplx);  // T slots (ring)
         const size_t gen1 = generic_t_bytes(p, 1);
         return fast > gen1 ? fast : gen1;
     }
-    return generic_t_bytes(p, batch);
+    return generic_t_bytes(p, batch);   // generic kernels: one focus value at a time
 }
+
+size_t litho_plan_workspace_bytes(const litho_plan_t* p, int batch) { return litho_plan_workspace_bytes_focus(p, batch, 1); }
 
 // coarse -> fine interpolation buffers of the fast path (see fine_plane_fast)
 struct FinalizeLayout {
@@ -987,23 +996,58 @@ int litho_abbe_fft_accumulate(const litho_plan_t* p, const void* maskFT, const v
                                         workspace_bytes, stream, 3);
 }
 
+static int accumulate_impl(const litho_plan_t* p, const void* maskFT, const void* pupil, int nf, size_t pupil_stride,
+                           const int32_t* shifts, const float* weights, int n_src, int batch, float* intensity,
+                           size_t intensity_stride, void* workspace, size_t workspace_bytes, void* stream, int phases);
+
 int litho_abbe_fft_accumulate_ex(const litho_plan_t* p, const void* maskFT, const void* pupil, const int32_t* shifts,
                                  const float* weights, int n_src, int batch, float* intensity, void* workspace,
                                  size_t workspace_bytes, void* stream, int phases) {
+    return accumulate_impl(p, maskFT, pupil, 1, 0, shifts, weights, n_src, batch, intensity, 0, workspace,
+                           workspace_bytes, stream, phases);
+}
+
+int litho_abbe_fft_accumulate_focus(const litho_plan_t* p, const void* maskFT, const void* pupils, int n_focus,
+                                    size_t pupil_stride, const int32_t* shifts, const float* weights, int n_src,
+                                    int batch, float* intensities, size_t intensity_stride, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+    if (n_focus < 1 || n_focus > 4096) return fail(LITHO_ERR_ARG, "accumulate_focus: n_focus out of range");
+    if (p && n_focus > 1) {
+        if (pupil_stride < (size_t)p->pn * p->pn) return fail(LITHO_ERR_ARG, "accumulate_focus: pupil_stride < pn*pn");
+        if (intensity_stride < intensity_elems(p)) return fail(LITHO_ERR_ARG, "accumulate_focus: intensity_stride < plan.intensity_elems");
+    }
+    return accumulate_impl(p, maskFT, pupils, n_focus, pupil_stride, shifts, weights, n_src, batch, intensities,
+                           intensity_stride, workspace, workspace_bytes, stream, 3);
+}
+
+static int accumulate_impl(const litho_plan_t* p, const void* maskFT, const void* pupil, int nf, size_t pupil_stride,
+                           const int32_t* shifts, const float* weights, int n_src, int batch, float* intensity,
+                           size_t intensity_stride, void* workspace, size_t workspace_bytes, void* stream, int phases) {
     if (!p || !maskFT || !pupil || !intensity) return fail(LITHO_ERR_ARG, "accumulate: null argument");
     if (n_src < 0) return fail(LITHO_ERR_ARG, "accumulate: negative n_src");
     if (n_src == 0) return LITHO_OK;
     if (!shifts) return fail(LITHO_ERR_ARG, "accumulate: shifts is null");
+    if (p->path != 2 && nf > 1) {
+        // generic fine-grid kernels: one focus value at a time (same results, no sharing of the mask window)
+        for (int f = 0; f < nf; ++f) {
+            const int rc = accumulate_impl(p, maskFT, (const cplx*)pupil + (size_t)f * pupil_stride, 1, 0, shifts, weights,
+                                           n_src, batch, intensity + (size_t)f * intensity_stride, 0, workspace,
+                                           workspace_bytes, stream, phases);
+            if (rc) return rc;
+        }
+        return LITHO_OK;
+    }
     if (batch <= 0) {
         // default: the plan's batch, but at least 4 batches per call so that the row pass of one batch
         // overlaps the column pass of the previous one (short source lists, e.g. one rank's shard)
-        batch = p->default_batch;
+        batch = default_batch_focus(p, nf);
         const int q = (n_src + 3) / 4;
         if (q < batch) batch = q < 1 ? 1 : q;
     }
     if (batch > n_src) batch = n_src;
-    if (!workspace || workspace_bytes < litho_plan_workspace_bytes(p, batch))
+    if (!workspace || workspace_bytes < litho_plan_workspace_bytes_focus(p, batch, nf))
         return fail(LITHO_ERR_WORKSPACE, "accumulate: workspace too small for the requested batch");
+    if ((double)batch * nf * 2.0 * p->Sr >= 2.0e9) return fail(LITHO_ERR_ARG, "accumulate: batch * n_focus too large");
     // equal-sized batches (130 points with batch 16 -> 9 x 14..15 instead of 8 x 16 + a 2-point launch pair)
     {
         const int nbatches = (n_src + batch - 1) / batch;
@@ -1017,11 +1061,12 @@ int litho_abbe_fft_accumulate_ex(const litho_plan_t* p, const void* maskFT, cons
         fr.pupil = (const cplx*)pupil; fr.mask = (const cplx*)maskFT; fr.pn = p->pn;
         fr.pr0 = p->bbox[0]; fr.pc0 = p->bbox[2]; fr.Sr = p->Sr; fr.Sc = p->Sc;
         fr.shifts = (const int2_*)shifts; fr.tables = p->tables; fr.T = (cplx*)workspace; fr.status = p->status;
+        fr.n_focus = nf; fr.pupil_stride = pupil_stride;
         FastColsParams fc;
         memset(&fc, 0, sizeof(fc));
         fc.T = (const cplx*)workspace; fc.Sr = p->Sr; fc.weights = weights; fc.tables = p->tables;
         fc.ic = intensity; fc.status = p->status;
-        const bool use_fused = p->fused && (phases & 3) == 3 &&
+        const bool use_fused = p->fused && nf == 1 && (phases & 3) == 3 &&
                                workspace_bytes >= 2 * (size_t)p->fused_B * 2 * p->Sr * p->Mf * sizeof(cplx);
         if (use_fused) {
             // one persistent launch per chunk of <= 65536 groups (counter capacity)
@@ -1064,7 +1109,9 @@ int litho_abbe_fft_accumulate_ex(const litho_plan_t* p, const void* maskFT, cons
         // of the other (both are short, ~20-40 us at cfg3).  rows(b) -> cols(b) and cols(b) -> rows(b+LITHO_TSLOTS)
         // (slot reuse) are ordered with events; all column passes stay on one stream, which also
         // serialises their read-modify-write of the intensity plane.
-        const size_t slot_elems = (size_t)batch * 2 * p->Sr * p->Mf;
+        const size_t focus_elems = (size_t)batch * 2 * p->Sr * p->Mf;   // T block of one focus value in a slot
+        const size_t slot_elems = focus_elems * nf;
+        fr.t_focus_stride = focus_elems;
         cplx* Tslot[LITHO_TSLOTS];
         for (int i = 0; i < LITHO_TSLOTS; ++i) Tslot[i] = (cplx*)workspace + (size_t)i * slot_elems;
         // one tensor map over the whole ring; a tile = Sr rows x tma_cols columns fetched in nbox boxes
@@ -1072,7 +1119,7 @@ int litho_abbe_fft_accumulate_ex(const litho_plan_t* p, const void* maskFT, cons
             // <= 4 boxes of M/4 rows cover the rows u < M that exist; the rim row u = M (Sr == M+1) is a 1-D copy
             const int body = p->Sr > p->Mf ? p->Mf : p->Sr;
             const int nbox = (body + p->tma_box_rows - 1) / p->tma_box_rows;
-            if (make_tile_map(&fc.tile, workspace, p->Mf, (long long)LITHO_TSLOTS * batch * 2 * p->Sr, p->tma_box_rows,
+            if (make_tile_map(&fc.tile, workspace, p->Mf, (long long)LITHO_TSLOTS * nf * batch * 2 * p->Sr, p->tma_box_rows,
                               p->tma_cols) == 0) {
                 fc.use_tma = p->tma_cols;
                 fc.nbox = nbox;
@@ -1087,44 +1134,57 @@ int litho_abbe_fft_accumulate_ex(const litho_plan_t* p, const void* maskFT, cons
         // plane): its only dependencies are the column passes that last read each ring slot, which the plan's
         // events already track when the ring is the one the previous call used.
         const bool chained = overlap && (phases & LITHO_PHASE_INPUTS_READY) && p->last_ws == workspace &&
-                             p->last_batch == batch;
+                             p->last_batch == batch * nf;
         if (overlap && !chained) {
             BE_CHECK((int)cudaEventRecord(p->ev_start, st));
             BE_CHECK((int)cudaStreamWaitEvent(p->aux_stream, p->ev_start, 0));
             for (int i = 0; i < LITHO_TSLOTS; ++i) p->cols_recorded[i] = 0;
         }
         p->last_ws = overlap ? workspace : nullptr;   // single-pass (profiling) calls break the chain
-        p->last_batch = batch;
+        p->last_batch = batch * nf;
 #else
         const bool overlap = false;
 #endif
         int b = 0;
         for (int s0 = 0; s0 < n_src; s0 += batch, ++b) {
             const int nb = (n_src - s0) < batch ? (n_src - s0) : batch;
-            fr.s_begin = s0; fr.batch = nb; fr.T = Tslot[b % LITHO_TSLOTS];
-            fc.s_begin = s0; fc.batch = nb; fc.T = Tslot[b % LITHO_TSLOTS];
-            fc.row_begin = (long long)(b % LITHO_TSLOTS) * batch * 2 * p->Sr;
+            const int slot = b % LITHO_TSLOTS;
+            fr.s_begin = s0; fr.batch = nb; fr.T = Tslot[slot];
+            fc.s_begin = s0; fc.batch = nb;
+            // one column pass per focus value: its T block is a contiguous [nb][2][Sr][M] batch, its plane its own
+            auto cols_all = [&](litho_stream_t cs) -> int {
+                for (int f = 0; f < nf; ++f) {
+                    fc.T = Tslot[slot] + (size_t)f * focus_elems;
+                    fc.row_begin = ((long long)slot * nf + f) * batch * 2 * p->Sr;
+                    fc.ic = intensity + (size_t)f * intensity_stride;
+                    const int rc = dispatch_fast_cols(p->Mf, p->ppt, fc, cs);
+                    if (rc) return rc;
+                }
+                return 0;
+            };
 #if !defined(LITHO_EMU)
             if (overlap) {
-                if (p->cols_recorded[b % LITHO_TSLOTS])
-                    BE_CHECK((int)cudaStreamWaitEvent(p->aux_stream, p->ev_cols[b % LITHO_TSLOTS], 0));
+                if (p->cols_recorded[slot])
+                    BE_CHECK((int)cudaStreamWaitEvent(p->aux_stream, p->ev_cols[slot], 0));
                 BE_CHECK(dispatch_fast_rows(p->Mf, p->ppt, fr, p->n_sm * (p->ppt == 16 ? 4 : 2), p->aux_stream));
-                BE_CHECK((int)cudaEventRecord(p->ev_rows[b % LITHO_TSLOTS], p->aux_stream));
-                BE_CHECK((int)cudaStreamWaitEvent(st, p->ev_rows[b % LITHO_TSLOTS], 0));
-                BE_CHECK(dispatch_fast_cols(p->Mf, p->ppt, fc, st));
-                BE_CHECK((int)cudaEventRecord(p->ev_cols[b % LITHO_TSLOTS], st));
-                p->cols_recorded[b % LITHO_TSLOTS] = 1;
+                BE_CHECK((int)cudaEventRecord(p->ev_rows[slot], p->aux_stream));
+                BE_CHECK((int)cudaStreamWaitEvent(st, p->ev_rows[slot], 0));
+                BE_CHECK(cols_all(st));
+                BE_CHECK((int)cudaEventRecord(p->ev_cols[slot], st));
+                p->cols_recorded[slot] = 1;
                 continue;
             }
 #endif
             if (phases & 1) BE_CHECK(dispatch_fast_rows(p->Mf, p->ppt, fr, p->n_sm * (p->ppt == 16 ? 4 : 2), st));
-            if (phases & 2) BE_CHECK(dispatch_fast_cols(p->Mf, p->ppt, fc, st));
+            if (phases & 2) BE_CHECK(cols_all(st));
         }
         }
-        if ((phases & 2) && p->q > 1 && (p->er >= 0 || p->ec >= 0)) {
+        if ((phases & 2) && p->q > 1 && (p->er >= 0 || p->ec >= 0))
+        for (int f = 0; f < nf; ++f) {
+            float* const intensity_f = intensity + (size_t)f * intensity_stride;
             RimParams rm;
             memset(&rm, 0, sizeof(rm));
-            rm.pupil = (const cplx*)pupil; rm.mask = (const cplx*)maskFT; rm.pn = p->pn;
+            rm.pupil = (const cplx*)pupil + (size_t)f * pupil_stride; rm.mask = (const cplx*)maskFT; rm.pn = p->pn;
             rm.pr0 = p->bbox[0]; rm.pc0 = p->bbox[2]; rm.Sr = p->Sr; rm.Sc = p->Sc; rm.M = p->Mf;
             rm.shifts = (const int2_*)shifts; rm.weights = weights; rm.n_src = n_src;
             memcpy(rm.ext, p->ext, sizeof(rm.ext));
@@ -1137,7 +1197,7 @@ int litho_abbe_fft_accumulate_ex(const litho_plan_t* p, const void* maskFT, cons
             rm.frow = p->rim_scratch; rm.fcol = p->rim_scratch + rim_row_floats(p); rm.stride = p->rim_stride;
             RimReduceParams rr;
             rr.slices = p->rim_scratch; rr.stride = p->rim_stride; rr.n_slices = ctas; rr.n = (int)p->rim_stride;
-            rr.plane = rim_row_ptr(p, intensity);
+            rr.plane = rim_row_ptr(p, intensity_f);
             // shared memory: the longest (lo, hi) pair of lines that gets correlated
             int longest = 1;
             for (int axis = 0; axis < 2; ++axis) {

@@ -295,13 +295,13 @@ def abbe_image_sharded(mask, maskFT, pupilF, lightsource, pixelSize, deltaK, wav
 
 
 def focus_sweep_sharded(mask, maskFT, pupils, lightsource, pixelSize, deltaK, wavelength, device, *, group=None,
-                        batch: int = 0):
+                        batch: int = 0, focus_batch: int = 0):
     """Focus-exposure sweep (BASELINE cfg5): one aerial image per pupil function in `pupils`, the pupils
     (focus values) sharded across the ranks -- independent images, so no reduce; every rank returns the
     full list (images of other ranks are received with one all_gather per image slot).
 
-    With a single process it is simply a loop over the pupils that reuses the uploaded mask spectrum and
-    source-point list."""
+    The focus values of one rank are batched (AbbeEngine.abbe_fft_focus; `focus_batch` caps how many share one row
+    pass, 0 = all of them)."""
     dev = _require_cuda(device)
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank(group) if world > 1 else 0
@@ -311,13 +311,14 @@ def focus_sweep_sharded(mask, maskFT, pupils, lightsource, pixelSize, deltaK, wa
         pn = int(maskFT_d.shape[0])
         eps, N = epsilon_n(deltaK, pixelSize, wavelength)
         shifts_d = source_shifts(lightsource.to(dev), pn)
+        # this rank's focus values are imaged together: one row pass per batch of source points serves all of them
+        # (litho_abbe_fft_accumulate_focus), so the shifted mask-spectrum window is fetched once per group
+        idx = list(range(rank, len(pupils), world))
         mine = {}
-        for i in range(rank, len(pupils), world):
-            pupil_d = _as_c64(pupils[i], dev)
-            plan = eng.plan_for(pn, N, eng.pupil_support(pupil_d), shifts_d)
-            intensity = eng.intensity_plane(plan)
-            eng.accumulate(plan, maskFT_d, pupil_d, shifts_d, intensity, None, batch)
-            mine[i] = eng.finalize(plan, intensity, eps)
+        if idx:
+            imgs = eng.abbe_fft_focus(maskFT_d, [pupils[i] for i in idx], None, pixelSize, deltaK, wavelength,
+                                      shifts=shifts_d, batch=batch, focus_batch=focus_batch)
+            mine = dict(zip(idx, imgs))
         if world == 1:
             return [mine[i] for i in range(len(pupils))]
         side = eng.plan(pn, N, (0, pn - 1, 0, pn - 1), generic=True).output_side(eps)

@@ -223,6 +223,59 @@ class AbbeEngine:
                 reduce_fn(intensity)
             return self.finalize(plan, intensity, eps) if postprocess else self.unpermute(plan, intensity)
 
+    def abbe_fft_focus(self, maskFT, pupils, lightsource, pixelSize, deltaK, wavelength, *, weights=None,
+                       batch: int = 0, shifts=None, postprocess: bool = True, focus_batch: int = 0):
+        """Focus batching (BASELINE cfg5): abbeImage(fft=True) for every pupil function in `pupils` (a list of
+        [pn, pn] tensors or one [F, pn, pn] tensor: focus / aberration variants of ONE pupil, i.e. the same support) with
+        the mask spectrum and the source shared.  One row pass per batch of source points serves `focus_batch` focus
+        values at a time (default: all of them), so each shifted mask-spectrum row is fetched once per group; then one
+        column pass per focus value.  Returns the list of images; each equals the single-image call bit for bit."""
+        dev = self.device
+        with torch.cuda.device(dev):
+            pn = _check_square("maskFT", maskFT)
+            maskFT_d = _as_c64(maskFT, dev)
+            if isinstance(pupils, torch.Tensor):
+                if pupils.dim() != 3 or tuple(pupils.shape[1:]) != (pn, pn):
+                    raise _native.LithoError(f"pupils must have shape [F, {pn}, {pn}], got {tuple(pupils.shape)}")
+                stack = _as_c64(pupils, dev)
+            else:
+                for q in pupils:
+                    _check_square("pupil", q, pn)
+                stack = torch.stack([_as_c64(q, dev) for q in pupils])
+            F = int(stack.shape[0])
+            if F == 0:
+                return []
+            eps, N = epsilon_n(deltaK, pixelSize, wavelength)
+            if shifts is None:
+                _check_square("lightsource", lightsource, pn)
+                shifts_d = source_shifts(lightsource.to(dev, non_blocking=True), pn)
+            else:
+                shifts_d = shifts.to(device=dev, dtype=torch.int32).contiguous()
+            n_src = int(shifts_d.shape[0])
+            w_d = None if weights is None else weights.to(device=dev, dtype=torch.float32).contiguous()
+            if w_d is not None and int(w_d.numel()) != n_src:
+                raise _native.LithoError(f"{int(w_d.numel())} weights for {n_src} source points")
+            # one plan for all focus values: they must share the support (window and rim extents)
+            support = self.pupil_support(stack[0])
+            for f in range(1, F):
+                if self.pupil_support(stack[f]) != support:
+                    raise _native.LithoError("abbe_fft_focus: the pupils do not share one support; image them one by one")
+            plan = self.plan_for(pn, N, support, shifts_d)
+            elems = plan.intensity_elems
+            stride = (elems + 63) // 64 * 64
+            planes = torch.zeros((F, stride), dtype=torch.float32, device=dev)
+            fb = F if focus_batch <= 0 else min(F, focus_batch)
+            if n_src:
+                for f0 in range(0, F, fb):
+                    nf = min(fb, F - f0)
+                    wsb = plan.workspace_bytes_focus(batch, nf)
+                    ws = self.workspace(wsb, ("t", plan.handle.value) if plan.path == 2 else "t")
+                    plan.accumulate_focus(maskFT_d.data_ptr(), stack[f0].data_ptr(), nf, pn * pn, shifts_d.data_ptr(),
+                                          None if w_d is None else w_d.data_ptr(), n_src, batch, planes[f0].data_ptr(),
+                                          stride, ws.data_ptr(), wsb, self.stream())
+            fin = self.finalize if postprocess else (lambda pl, it, e: self.unpermute(pl, it))
+            return [fin(plan, planes[f], eps) for f in range(F)]
+
     # -- pipelined form of abbe_fft: stage inputs one image ahead --------------------------------
     def prepare(self, maskFT, pupilF, lightsource, pixelSize, deltaK, wavelength, *, stream=None, slot: int = 0,
                 shard=None, generic: bool = False, plan: _native.Plan | None = None,

@@ -17,3 +17,9 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:abbe
     -o gpurun_out/${TAG}_prof python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/${TAG}_ncu_full.log 2>&1
 fi
 tail -15 gpurun_out/${TAG}_gpu_tests.log | cut -c1-300; cat gpurun_out/${TAG}_smoke.log | tail -2; tail -c 5000 gpurun_out/${TAG}_bench.log
+if [ "${OTHER_CONFIGS:-0}" = "1" ]; then
+for c in cfg4 cfg5; do
+  timeout 600 python bench.py --config $c --steps 3 --warmup 3 --no-cpu-baseline --no-library-baseline > gpurun_out/${TAG}_bench_$c.log 2>&1
+  echo "== $c"; tail -1 gpurun_out/${TAG}_bench_$c.log | cut -c1-600
+done
+fi

@@ -346,3 +346,75 @@ def test_emu_rejects_unsupported():
         lib.plan_create(256, 128, (0, 255, 0, 255))    # N < pn: the reference raises too (Q7)
     with pytest.raises(Exception):
         lib.plan_create(64, 100, (0, 63, 0, 63))       # N not a power of two
+
+
+@pytest.mark.parametrize("name,fast", [("demo64_quasar", True), ("wrap_128", False)])
+@pytest.mark.parametrize("tma", ["1", "0"])
+def test_emu_focus_batching_equals_single_images(monkeypatch, name, fast, tma):
+    """litho_abbe_fft_accumulate_focus (f1: one row pass serves all focus values, one column pass per focus value)
+    against n_focus separate litho_abbe_fft_accumulate calls: bit-identical planes, on the fast path (TMA-staged and
+    plain column kernels, uneven batches so the T ring wraps) and on the generic fallback; status words stay clear."""
+    monkeypatch.setenv("LITHO_TMA", tma)
+    c = KAT[name]
+    lib = H.emu_lib()
+    pn = c["maskFT"].shape[0]
+    _, N = lib.epsilon_n(4 / pn, float(c["pixel_size"]), 193.0)
+    mft = np.ascontiguousarray(c["maskFT"], np.complex64)
+    base = np.ascontiguousarray(c["pupil"], np.complex64)
+    # focus variants of one pupil: same support, different phase (defocus ~ r^2)
+    yy, xx = np.mgrid[0:pn, 0:pn]
+    r2 = ((yy - pn / 2) ** 2 + (xx - pn / 2) ** 2) / (pn / 4) ** 2
+    F = 3
+    pupils = np.ascontiguousarray(np.stack([base * np.exp(1j * 0.7 * f * r2) for f in range(F)]).astype(np.complex64))
+    shifts = np.ascontiguousarray(O.source_shifts(c["lightsource"], pn)[::3][:11], np.int32)
+    w = np.linspace(0.5, 1.5, len(shifts)).astype(np.float32)
+    support = lib.pupil_support(base.ctypes.data, pn)
+    plan = lib.plan_create(pn, N, support, 0 if fast else 1)
+    assert plan.path == (2 if fast else 1)
+    elems = plan.intensity_elems
+    stride = elems + 5
+    for batch in (0, 2):
+        wsb = plan.workspace_bytes_focus(batch, F)
+        ws = np.zeros(max(wsb, 8), np.uint8)
+        planes = np.zeros((F, stride), np.float32)
+        plan.accumulate_focus(mft.ctypes.data, pupils.ctypes.data, F, pn * pn, shifts.ctypes.data, w.ctypes.data,
+                              len(shifts), batch, planes.ctypes.data, stride, ws.ctypes.data, wsb)
+        for f in range(F):
+            single = np.zeros(elems, np.float32)
+            wsb1 = plan.workspace_bytes(batch)
+            ws1 = np.zeros(max(wsb1, 8), np.uint8)
+            plan.accumulate(mft.ctypes.data, pupils[f].ctypes.data, shifts.ctypes.data, w.ctypes.data, len(shifts),
+                            batch, single.ctypes.data, ws1.ctypes.data, wsb1)
+            assert np.array_equal(planes[f, :elems], single), (batch, f)
+            assert not planes[f, elems:].any()
+    assert plan.status() == (0, 0)
+    # and against the oracle for one focus value
+    out = np.zeros((pn, pn), np.float32)
+    fwb = plan.finalize_workspace_bytes()
+    fws = np.zeros(max(fwb, 8), np.uint8)
+    plan.unpermute(planes[1].ctypes.data, out.ctypes.data, fws.ctypes.data, fwb)
+    ref = np.zeros((pn, pn))
+    for (d0, d1), wi in zip(shifts, w):
+        ref += wi * np.abs(O.calculate_fft_aerial(np.roll(pupils[1], (int(d0), int(d1)), (0, 1)), mft, pn, N)) ** 2
+    assert O.rel_l2(out, ref) < H.TOL
+    plan.close()
+
+
+def test_emu_status_word_reports_clamped_shift():
+    """A fast plan driven outside its no-wrap contract through the raw C ABI: memory-safe, and litho_plan_status
+    reports it (read-and-clear)."""
+    c = KAT["demo64_quasar"]
+    lib = H.emu_lib()
+    mft = np.ascontiguousarray(c["maskFT"], np.complex64)
+    pup = np.ascontiguousarray(c["pupil"], np.complex64)
+    _, N = lib.epsilon_n(4 / 64, 25.0, 193.0)
+    plan = lib.plan_create(64, N, lib.pupil_support(pup.ctypes.data, 64))
+    assert plan.path == 2 and plan.status() == (0, 0)
+    bad = np.array([[0, 0], [40, 0]], np.int32)
+    inten = np.zeros(plan.intensity_elems, np.float32)
+    wsb = plan.workspace_bytes(2)
+    ws = np.zeros(wsb, np.uint8)
+    plan.accumulate(mft.ctypes.data, pup.ctypes.data, bad.ctypes.data, None, 2, 2, inten.ctypes.data, ws.ctypes.data, wsb)
+    assert plan.status() == (1, 0)
+    assert plan.status() == (0, 0)
+    plan.close()

@@ -714,3 +714,68 @@ def test_builders_match_reference_on_this_gpu(L, dev):
         ours = L.Mask(g, ps, dev).fraunhofer(193.0, True)
         ref = R["mask"].Mask(g.to(dev), ps, dev).fraunhofer(193.0, True)
         assert float((ours - ref).abs().max() / ref.abs().max()) < 2e-6, (pn, ps)
+
+
+def test_focus_batching_16_values_equals_single_images(L, dev):
+    """f1 (BASELINE cfg5 semantics at 256 px): 16 defocus values through AbbeEngine.abbe_fft_focus -- one row pass
+    serves all focus values, one column pass each -- against 16 single abbeImage calls (bit-identical) and the
+    oracle's float64 image for three of them; also in groups of 5 (ragged last group)."""
+    from lithographysimulator_b200.imaging import AbbeEngine
+    cfg, mft, _, ls = _cfg_inputs("cfg1")
+    eng = AbbeEngine.get(dev)
+    pn = cfg.pn
+    mft_d, ls_d = _t(mft, dev), _t(ls, dev)
+    m = _mask_stub(L, pn, cfg.pixel_size, dev)
+    pupils = []
+    for d in np.linspace(-150, 150, 16):
+        ab = torch.tensor([0, 0, 0.01, 0, float(d), 0.01, 0, 0.01, 0.01, 0.01], dtype=torch.float16, device=dev)
+        pupils.append(L.Pupil(pn, cfg.wavelength, cfg.na, ab, dev).generatePupilFunction())
+    args = (cfg.pixel_size, 4 / pn, cfg.wavelength)
+    together = eng.abbe_fft_focus(mft_d, pupils, ls_d, *args)
+    grouped = eng.abbe_fft_focus(mft_d, torch.stack(pupils), ls_d, *args, focus_batch=5)
+    assert len(together) == 16 and len(grouped) == 16
+    for f, pf in enumerate(pupils):
+        single = L.abbeImage(m, mft_d, pf, ls_d, *args, True, dev)
+        assert torch.equal(together[f], single), f
+        assert torch.equal(grouped[f], single), f
+        if f in (0, 7, 15):
+            ref = O.abbe_image(mft, pf.cpu().numpy(), ls, cfg.pixel_size, 4 / pn, cfg.wavelength, True, np.complex128)
+            assert O.rel_l2(together[f].cpu().numpy(), ref) < H.TOL
+    # pupils with different supports are refused
+    small = pupils[0].clone()
+    small[: pn // 2 - 10] = 0
+    from lithographysimulator_b200 import _native
+    with pytest.raises(_native.LithoError):
+        eng.abbe_fft_focus(mft_d, [pupils[0], small], ls_d, *args)
+
+
+def test_cfg5_focus_pair_against_reference_golden(L, dev, golden_dir):
+    """The first two focus values of the BASELINE cfg5 sweep (8192 px, 980 source points, sub-FFT 4096) imaged
+    together through the focus-batched path; focus 0 against the unmodified reference's full image
+    (tests/golden/cfg5.npz), focus 1 against the single-image call."""
+    import os
+    from lithographysimulator_b200.imaging import AbbeEngine
+    path = f"{golden_dir}/cfg5.npz"
+    if not os.path.exists(path):
+        pytest.skip(f"{path} not generated")
+    z = np.load(path)
+    cfg = wl.CONFIGS["cfg5"]
+    pn, st = cfg.pn, int(z["sample_stride"])
+    eng = AbbeEngine.get(dev)
+    mask = L.Mask(torch.from_numpy(cfg.geometry()), cfg.pixel_size, dev)
+    mft = mask.fraunhofer(cfg.wavelength, True)
+    src = L.LightSource(cfg.sigma_in, cfg.sigma_out, pn, cfg.na, 0, 0, dev)
+    ls = src.generateQuasar(4, -math.pi / 8) * torch.from_numpy(wl.lattice(pn, cfg.stride)).to(dev)
+    pupils = []
+    for d in cfg.defocus_sweep[:2]:
+        ab = list(z["aberrations"])
+        ab[4] = d
+        pupils.append(L.Pupil(pn, cfg.wavelength, cfg.na, torch.tensor(ab, dtype=torch.float16, device=dev), dev)
+                      .generatePupilFunction())
+    assert float(z["aberrations"][4]) == cfg.defocus_sweep[0]
+    imgs = eng.abbe_fft_focus(mft, pupils, ls, cfg.pixel_size, mask.deltaK, cfg.wavelength)
+    assert tuple(imgs[0].shape) == tuple(z["shape"])
+    assert O.rel_l2(imgs[0][::st, ::st].cpu().numpy(), z["image_sample"]) < H.TOL
+    assert abs(float(imgs[0].sum(dtype=torch.float64)) / float(z["img_sum"]) - 1) < 1e-5
+    single = L.abbeImage(mask, mft, pupils[1], ls, cfg.pixel_size, mask.deltaK, cfg.wavelength, True, dev)
+    assert torch.equal(imgs[1], single)
