@@ -58,7 +58,7 @@ def build_inputs_device(cfg_name: str, dev):
     src = L.LightSource(cfg.sigma_in, cfg.sigma_out, cfg.pn, cfg.na, 0, 0, dev)
     ls = src.generateQuasar(4, -math.pi / 8) if cfg.source == "quasar" else src.generateAnnular()
     ls = ls * torch.from_numpy(wl.lattice(cfg.pn, cfg.stride)).to(dev)
-    ab = torch.tensor(cfg.aberrations, dtype=torch.float16, device=dev)
+    ab = torch.tensor(wl.aberrations_of(cfg), dtype=torch.float16, device=dev)
     pf = L.Pupil(cfg.pn, cfg.wavelength, cfg.na, ab, dev).generatePupilFunction()
     torch.cuda.synchronize(dev)
     return cfg, mft, pf, ls
@@ -77,7 +77,7 @@ def build_inputs_host(cfg_name: str):
     else:
         ls = O.light_source_annular(cfg.sigma_in, cfg.sigma_out, cfg.pn)
     ls = (ls * wl.lattice(cfg.pn, cfg.stride)).astype(np.int64)
-    pf, _ = O.pupil_function(cfg.aberrations, cfg.pn, cfg.na, cfg.wavelength)
+    pf, _ = O.pupil_function(wl.aberrations_of(cfg), cfg.pn, cfg.na, cfg.wavelength)
     return cfg, mft, pf.astype(np.complex64), ls
 
 

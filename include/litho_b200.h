@@ -96,7 +96,7 @@ size_t litho_plan_workspace_bytes(const litho_plan_t* plan, int batch);
 int litho_plan_status(const litho_plan_t* plan, int* status_host, void* stream);
 /* Columns per tile of the TMA-staged column-pass kernel this plan launches (the T tile of the next source
  * point is copied global -> shared by cp.async.bulk.tensor while the current FFT runs); 0 when the plan
- * uses the plain-load column kernel (generic path, sub-FFT > 1024, LITHO_TMA=0, or a driver without
+ * uses the plain-load column kernel (generic path, LITHO_TMA=0, or a driver without
  * cuTensorMapEncodeTiled). */
 int litho_plan_column_tile(const litho_plan_t* plan);
 

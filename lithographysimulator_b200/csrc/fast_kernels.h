@@ -395,17 +395,23 @@ struct TmaShape {
     static constexpr int PRE_N = M / 2 + 1;
     static constexpr int TW1_OFF = (PRE_N + 1) & ~1;
     static constexpr int TW2_OFF = TW1_OFF + (F::R1 - 1) * F::NS1;
-    static constexpr int NTAB = TW2_OFF + (F::R2 - 1) * F::NS2;
+    static constexpr int NTAB = TW2_OFF + (F::R2 - 1) * F::NS2;      // device table: pre, tw1, tw2
     static constexpr int NTAB_PAD = (NTAB + 1) & ~1;
-    static constexpr int BOX_ROWS = M / 4 > 256 ? 256 : M / 4;     // rows per TMA box (<= 4 boxes cover u < M)
+    // M = 4096: exchange buffer (135 KB) + tile (66 KB) + all tables (49 KB) exceed the 227 KB of a CTA.  The
+    // third-pass table tw2 (3 x 1024 entries, indexed by k = thread-varying) then stays in global memory and is
+    // read through L1 (same LSU cost as a shared-memory read); pre and tw1 stay in shared memory.
+    static constexpr bool TW2_GLOBAL = (M >= 4096);
+    static constexpr int NTAB_SMEM = TW2_GLOBAL ? TW2_OFF : NTAB;
+    static constexpr int NTAB_SMEM_PAD = (NTAB_SMEM + 1) & ~1;
+    static constexpr int BOX_ROWS = M / 4 > 256 ? 256 : M / 4;     // rows per TMA box (boxes of <= 256 rows cover u < M)
     static constexpr size_t EX_BYTES = (size_t)2 * CBT * Sh::SMEM_ELEMS * sizeof(cplx);
-    static constexpr size_t TILE_OFF = ((size_t)NTAB_PAD * sizeof(cplx) + EX_BYTES + 127) / 128 * 128;
+    static constexpr size_t TILE_OFF = ((size_t)NTAB_SMEM_PAD * sizeof(cplx) + EX_BYTES + 127) / 128 * 128;
     static constexpr size_t TILE_BYTES = ((size_t)(M + 1 + RIM_EXTRA) * CBT * sizeof(cplx) + 15) / 16 * 16;
     static constexpr size_t BAR_OFF = TILE_OFF + TILE_BYTES;
     static constexpr size_t SMEM = BAR_OFF + 48;  // mbarrier (8, padded to 16) + TileCtl
-    // a box must be a multiple of 128 bytes (TMA destination alignment) and a half at least one warp... no: the
-    // halves only meet at CTA barriers, so any THREADS that is a multiple of 32 works
-    static constexpr bool OK = PPT == 32 && M >= 32 && M <= 2048 && CBT >= 2 && (M % CBT) == 0 &&
+    // a box must be a multiple of 128 bytes (TMA destination alignment); the halves only meet at CTA barriers, so
+    // any THREADS that is a multiple of 32 works
+    static constexpr bool OK = PPT == 32 && M >= 32 && M <= 4096 && CBT >= 2 && (M % CBT) == 0 &&
                                ((size_t)BOX_ROWS * CBT * sizeof(cplx)) % 128 == 0 && THREADS % 32 == 0 &&
                                THREADS <= 512 && SMEM <= 227 * 1024;
     // two CTAs per SM when registers (128/thread) and shared memory (+1 KB reserved per CTA) allow
@@ -414,12 +420,14 @@ struct TmaShape {
 
 template <int M, int PPT, int CBT>
 struct TmaTw {
-    const cplx* tab;
+    const cplx* tab;    // shared memory: pre, tw1 (and tw2 unless TW2_GLOBAL)
+    const cplx* gtab;   // the same table in global memory (device copy of the plan)
     template <int PASS>
     LITHO_HD cplx get(int t, int k) const {
         using S = TmaShape<M, PPT, CBT>;
         using F = FastShape<M, PPT>;
         if constexpr (PASS == 1) return tab[S::TW1_OFF + (t - 1) * F::NS1 + k];
+        else if constexpr (S::TW2_GLOBAL) return ldg_c(gtab + S::TW2_OFF + (t - 1) * F::NS2 + k);
         else return tab[S::TW2_OFF + (t - 1) * F::NS2 + k];
     }
 };
@@ -466,7 +474,7 @@ LITHO_HD void fast_cols_tma_body(const FastColsParams& P, const Ctx& ctx, unsign
     cplx* tab = smem;
     const cplx* tile = reinterpret_cast<const cplx*>(smem_raw + S::TILE_OFF);
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + S::BAR_OFF);
-    for (int i = ctx.tid(); i < S::NTAB_PAD / 2; i += ctx.bdim()) ctx.cp_async16(tab + 2 * i, P.tables_c + 2 * i);
+    for (int i = ctx.tid(); i < S::NTAB_SMEM_PAD / 2; i += ctx.bdim()) ctx.cp_async16(tab + 2 * i, P.tables_c + 2 * i);
     constexpr int NBLK = M / CBT;
     const int rc = ctx.bx() / NBLK;
     const int kc0 = (ctx.bx() - rc * NBLK) * CBT;
@@ -484,7 +492,7 @@ LITHO_HD void fast_cols_tma_body(const FastColsParams& P, const Ctx& ctx, unsign
     const int g = th / CBT;
     cplx* ex = smem + S::NTAB_PAD + (size_t)half * (CBT * F::Sh::SMEM_ELEMS) + col;
     const int rr = half;
-    const TmaTw<M, PPT, CBT> tw{tab};
+    const TmaTw<M, PPT, CBT> tw{tab, P.tables_c};
     const GroupSync<Ctx, 2> gs{ctx, 0, 0};
     const TileHook<Ctx> hook{ctx, smem_raw, &P, S::TILE_OFF, S::BAR_OFF, M * CBT};
 

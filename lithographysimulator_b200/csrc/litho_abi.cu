@@ -748,7 +748,7 @@ int litho_plan_create_lines(int pn, int N, const int* bbox, int lines, int flags
             }
         }
         p->path = 2; p->Mf = Mf; p->Nc = 2 * Mf; p->q = N / (2 * Mf);
-        // TMA-staged column kernel where the shape has one (M <= 1024).  LITHO_TMA=0 selects plain loads,
+        // TMA-staged column kernel where the shape has one (32 <= M <= 4096).  LITHO_TMA=0 selects plain loads,
         // LITHO_COL_NARROW=0/1 the wide (one 512-thread CTA per SM) or narrow (two 256-thread CTAs) tile.
         {
             // measured (profiles/README.md, r02f/r02g): narrow wins at M = 1024 (+3.8 %) and M = 128 (+9 %),

@@ -72,6 +72,15 @@ class Config:
         return {"line_space": line_space, "contacts": contacts, "manhattan": manhattan}[self.mask](self.pn)
 
 
+def aberrations_of(cfg: "Config", focus_index: int = 0) -> list:
+    """Aberration list of one image of the config: cfg5 (a focus sweep) puts defocus_sweep[focus_index] in slot 4
+    (the golden image tests/golden/cfg5.npz is the first focus value); the other configs have a single pupil."""
+    ab = list(cfg.aberrations)
+    if cfg.defocus_sweep:
+        ab[4] = cfg.defocus_sweep[focus_index]
+    return ab
+
+
 CONFIGS = {
     "cfg1": Config("cfg1", 256, "line_space", "annular", 0.6, 0.9, 8, aberrations=[0, 0, 0, 0, 50]),
     "cfg2": Config("cfg2", 1024, "contacts", "quasar", 0.4, 0.8, 11),

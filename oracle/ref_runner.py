@@ -53,7 +53,7 @@ def build_inputs(cfg, device):
     src = R["lightsource"].LightSource(cfg.sigma_in, cfg.sigma_out, cfg.pn, cfg.na, 0, 0, device)
     ls = src.generateQuasar(4, -math.pi / 8) if cfg.source == "quasar" else src.generateAnnular()
     ls = ls * torch.from_numpy(wl.lattice(cfg.pn, cfg.stride)).to(device)
-    ab = torch.tensor(cfg.aberrations, dtype=torch.float16, device=device)
+    ab = torch.tensor(wl.aberrations_of(cfg), dtype=torch.float16, device=device)
     pf = R["pupil"].Pupil(cfg.pn, cfg.wavelength, cfg.na, ab, device).generatePupilFunction()
     return m, mft, pf, ls
 
