@@ -490,7 +490,7 @@ LITHO_HD void fast_cols_tma_body(const FastColsParams& P, const Ctx& ctx, unsign
     const int th = ctx.tid() - half * S::HALF;
     const int col = th % CBT;
     const int g = th / CBT;
-    cplx* ex = smem + S::NTAB_PAD + (size_t)half * (CBT * F::Sh::SMEM_ELEMS) + col;
+    cplx* ex = smem + S::NTAB_SMEM_PAD + (size_t)half * (CBT * F::Sh::SMEM_ELEMS) + col;
     const int rr = half;
     const TmaTw<M, PPT, CBT> tw{tab, P.tables_c};
     const GroupSync<Ctx, 2> gs{ctx, 0, 0};

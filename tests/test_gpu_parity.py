@@ -779,3 +779,43 @@ def test_cfg5_focus_pair_against_reference_golden(L, dev, golden_dir):
     assert abs(float(imgs[0].sum(dtype=torch.float64)) / float(z["img_sum"]) - 1) < 1e-5
     single = L.abbeImage(mask, mft, pupils[1], ls, cfg.pixel_size, mask.deltaK, cfg.wavelength, True, dev)
     assert torch.equal(imgs[1], single)
+
+
+@pytest.mark.parametrize("name", ["cfg4", "cfg5"])
+def test_tma_column_pass_large_subfft_multi_tile(L, dev, name):
+    """Sub-FFT 2048 / 4096 (cfg4 / cfg5 grids): the TMA-staged column pass with several source points per launch
+    (tile of point sl+1 copied while the FFT of sl runs; at 4096 the exchange buffer, the tile and the tables fill
+    the 227 KB of the CTA and the third-pass twiddles come from global memory) against the plain-load kernel, with
+    batches of 2 so that the 3-slot T ring wraps."""
+    import os
+    from lithographysimulator_b200 import _native
+    cfg = wl.CONFIGS[name]
+    lib = _native.device_lib()
+    pn, N = cfg.pn, 2 * cfg.pn
+    mft_d = L.Mask(torch.from_numpy(cfg.geometry()), cfg.pixel_size, dev).fraunhofer(cfg.wavelength, True)
+    ab = torch.tensor(wl.aberrations_of(cfg), dtype=torch.float16, device=dev)
+    pf_d = L.Pupil(pn, cfg.wavelength, cfg.na, ab, dev).generatePupilFunction()
+    sh = torch.tensor([[0, 0], [pn // 5, -pn // 7], [-pn // 6, pn // 9], [17, 3], [-pn // 8, -pn // 8], [5, pn // 5],
+                       [-3, 1]], dtype=torch.int32, device=dev)
+    w = torch.linspace(0.5, 2.0, sh.shape[0], device=dev)
+    support = lib.pupil_support(pf_d.data_ptr(), pn, 0)
+    outs = {}
+    for tma in ("1", "0"):
+        os.environ["LITHO_TMA"] = tma
+        try:
+            plan = lib.plan_create(pn, N, support)
+        finally:
+            os.environ.pop("LITHO_TMA", None)
+        assert plan.path == 2 and (plan.column_tile() > 0) == (tma == "1"), (plan.path, plan.column_tile())
+        inten = torch.zeros(plan.intensity_elems, dtype=torch.float32, device=dev)
+        wsb = plan.workspace_bytes(2)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        plan.accumulate(mft_d.data_ptr(), pf_d.data_ptr(), sh.data_ptr(), w.data_ptr(), sh.shape[0], 2,
+                        inten.data_ptr(), ws.data_ptr(), wsb, torch.cuda.current_stream(dev).cuda_stream)
+        torch.cuda.synchronize(dev)
+        assert plan.status() == (0, 0)
+        outs[tma] = inten.clone()
+        plan.close()
+        del ws
+    a, b = outs["1"].double(), outs["0"].double()
+    assert float((a - b).norm() / b.norm()) < 1e-6
