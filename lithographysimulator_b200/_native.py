@@ -60,6 +60,7 @@ SYMBOLS = [
     ("litho_direct_workspace_bytes", C.c_size_t, [C.c_int, C.POINTER(C.c_int), C.c_int]),
     ("litho_direct_accumulate", C.c_int, [_P, _P, _P, C.c_int, C.POINTER(C.c_int), _P, _P, C.c_int, C.c_int, _P, _P,
                                           C.c_size_t, _P]),
+    ("litho_direct_status", C.c_int, [C.POINTER(C.c_int), _P]),
     ("litho_direct_field", C.c_int, [_P, _P, _P, C.c_int, C.POINTER(C.c_int), _P, _P, C.c_size_t, _P]),
     ("litho_direct_mask_spectrum", C.c_int, [_P, _P, C.c_int, _P, _P, C.c_size_t, _P]),
     ("litho_source_build", C.c_int, [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_double, _P, _P]),

@@ -17,6 +17,8 @@
 
 #if defined(LITHO_EMU)
 #include "emu_runtime.h"
+#else
+#include "direct_tc.h"
 #endif
 
 using namespace litho;
@@ -1567,10 +1569,61 @@ int litho_direct_operator(int pn, double pixelSize, double wavelength, int sign,
     return LITHO_OK;
 }
 
+// Tensor-core path of litho_direct_accumulate (direct_tc.cu): on by default in the device build, LITHO_DIRECT_TC=0
+// selects the FP32 CUDA-core kernels (also used by the field / mask-spectrum entry points and the CPU emulation).
+static bool direct_tc_enabled(int pn) {
+#if defined(LITHO_EMU)
+    (void)pn;
+    return false;
+#else
+    if (pn < 64) return false;
+    const char* env = getenv("LITHO_DIRECT_TC");
+    return !(env && atoi(env) == 0);
+#endif
+}
+static int tc_upitch(int Sr) { return (Sr + 15) / 16 * 16; }
+
 size_t litho_direct_workspace_bytes(int pn, const int* bbox, int batch) {
     int Sr, Sc;
     if (direct_check(pn, bbox, &Sr, &Sc) || batch < 1) return 0;
-    return (size_t)batch * Sr * pn * sizeof(cplx);
+    const size_t fp32 = (size_t)batch * Sr * pn * sizeof(cplx);
+    const size_t tc = (size_t)batch * pn * tc_upitch(Sr) * sizeof(cplx) + (size_t)batch * pn * pn * sizeof(float);
+    return (direct_tc_enabled(pn) && tc > fp32) ? tc : fp32;
+}
+
+#if !defined(LITHO_EMU)
+static std::mutex g_tc_err_mutex;
+static std::map<int, int*> g_tc_err;
+static int* tc_err_word() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lock(g_tc_err_mutex);
+    auto it = g_tc_err.find(dev);
+    if (it != g_tc_err.end()) return it->second;
+    int* d = nullptr;
+    if (cudaMalloc((void**)&d, sizeof(int)) != cudaSuccess) return nullptr;
+    cudaMemset(d, 0, sizeof(int));
+    g_tc_err[dev] = d;
+    return d;
+}
+#endif
+
+int litho_direct_status(int* status_host, void* stream) {
+    if (!status_host) return fail(LITHO_ERR_ARG, "direct_status: null argument");
+    *status_host = 0;
+#if !defined(LITHO_EMU)
+    int* d = tc_err_word();
+    if (!d) return fail(LITHO_ERR_CUDA, "direct_status: no error word");
+    BE_CHECK(be_d2h_sync(status_host, d, sizeof(int), (litho_stream_t)stream));
+    if (*status_host) {
+        const int zero = 0;
+        BE_CHECK(be_h2d(d, &zero, sizeof(int), (litho_stream_t)stream));
+        BE_CHECK((int)cudaStreamSynchronize((litho_stream_t)stream));
+    }
+#else
+    (void)stream;
+#endif
+    return LITHO_OK;
 }
 
 static int direct_launch(int kind, int epi, const DirectParams& P, litho_stream_t st) {
@@ -1616,6 +1669,30 @@ int litho_direct_accumulate(const void* A, const void* maskFT, const void* pupil
     if (batch > n_src) batch = n_src;
     if (!workspace || workspace_bytes < litho_direct_workspace_bytes(pn, bbox, batch))
         return fail(LITHO_ERR_WORKSPACE, "direct_accumulate: workspace too small");
+#if !defined(LITHO_EMU)
+    if (direct_tc_enabled(pn)) {
+        // tensor cores: both products as 3xTF32 real GEMMs with fp32 accumulation in tensor memory (direct_tc.cu)
+        litho_tc::TcParams T;
+        memset(&T, 0, sizeof(T));
+        T.A = (const float2*)A; T.pn = pn; T.pupil = (const float2*)pupil; T.mask = (const float2*)maskFT;
+        T.pr0 = bbox[0]; T.pc0 = bbox[2]; T.Sr = Sr; T.Sc = Sc;
+        T.shifts = (const int2*)shifts;
+        T.Upitch = tc_upitch(Sr);
+        float2* U = (float2*)workspace;
+        float* part = (float*)((char*)workspace + (size_t)batch * pn * T.Upitch * sizeof(cplx));
+        T.U = U; T.Uout = U; T.part = part; T.err = tc_err_word();
+        for (int s0 = 0; s0 < n_src; s0 += batch) {
+            const int nb = (n_src - s0) < batch ? (n_src - s0) : batch;
+            T.s_begin = s0;
+            T.stage = 1;
+            BE_CHECK(litho_tc::tc_launch(T, Sr, nb, (litho_stream_t)stream));
+            T.stage = 2;
+            BE_CHECK(litho_tc::tc_launch(T, pn, nb, (litho_stream_t)stream));
+            BE_CHECK(litho_tc::tc_reduce(part, weights, s0, nb, pn, intensity, (litho_stream_t)stream));
+        }
+        return LITHO_OK;
+    }
+#endif
     DirectParams P;
     memset(&P, 0, sizeof(P));
     P.A = (const cplx*)A; P.pn = pn; P.pupil = (const cplx*)pupil; P.mask = (const cplx*)maskFT;

@@ -4,7 +4,9 @@ DFT-as-GEMM small-grid variant, FP32 CUDA cores against tensor cores, MEASURED o
 
 Measurement aid, not part of the product.  For pn in 64/128/256 and the BASELINE cfg1-style inputs it reports
 
-  * ours_fp32        litho_direct_accumulate (csrc/direct_kernels.h: FP32 CUDA-core tiles), us per source point
+  * ours_fp32        litho_direct_accumulate with LITHO_DIRECT_TC=0 (csrc/direct_kernels.h: FP32 CUDA-core tiles)
+  * ours_tc          litho_direct_accumulate, default for pn >= 64 (csrc/direct_tc.cu: tcgen05.mma kind::tf32, 3xTF32,
+                     fp32 accumulation in tensor memory), us per source point
   * ours_fft         the FFT-approximation path on the same grid (what the FFT path costs there), us per point
   * tc_tf32x1/x3     the same two complex products per source point as real block GEMMs on the tensor cores
                      (torch.bmm with TF32 enabled = cuBLAS tcgen05 kernels; the launch names are in the ncu list):
@@ -15,6 +17,7 @@ Measurement aid, not part of the product.  For pn in 64/128/256 and the BASELINE
     python scripts/direct_bench.py [--pn 64 128 256] [--points 64]
 """
 import argparse
+import ctypes as C
 import json
 import math
 import os
@@ -110,9 +113,20 @@ def main():
             return float((x.double() - ref64).norm() / ref64.norm())
 
         out = {"pn": pn, "source_points": n, "pupil_window": [int(r1 - r0 + 1), int(c1 - c0 + 1)]}
+        os.environ["LITHO_DIRECT_TC"] = "0"       # FP32 CUDA-core kernels (csrc/direct_kernels.h)
         img = L.abbeImage(mask, mft, pf, ls, 25, mask.deltaK, 193.0, False, dev)
         out["ours_fp32_us_per_point"] = timed(lambda: L.abbeImage(mask, mft, pf, ls, 25, mask.deltaK, 193.0, False, dev)) / n
         out["ours_fp32_rel_l2_vs_f64"] = rel(img)
+        os.environ["LITHO_DIRECT_TC"] = "1"       # tcgen05 3xTF32 kernel (csrc/direct_tc.cu), the default for pn >= 64
+        img = L.abbeImage(mask, mft, pf, ls, 25, mask.deltaK, 193.0, False, dev)
+        out["ours_tc_us_per_point"] = timed(lambda: L.abbeImage(mask, mft, pf, ls, 25, mask.deltaK, 193.0, False, dev)) / n
+        out["ours_tc_rel_l2_vs_f64"] = rel(img)
+        st = C.c_int(0)
+        eng.lib.check(eng.lib.litho_direct_status(C.byref(st), 0), "litho_direct_status")
+        out["ours_tc_status"] = st.value
+        from lithographysimulator_b200 import direct as D
+        out["ours_tc_us_per_point_batch64"] = timed(
+            lambda: D.direct_abbe_image(mft, pf, ls, 25, 193.0, dev, batch=64)) / n
         mft_f = mask.fraunhofer(193.0, True)
         out["ours_fft_path_us_per_point"] = timed(lambda: L.abbeImage(mask, mft_f, pf, ls, 25, mask.deltaK, 193.0, True, dev)) / n
         torch.backends.cuda.matmul.allow_tf32 = False

@@ -819,3 +819,49 @@ def test_tma_column_pass_large_subfft_multi_tile(L, dev, name):
         del ws
     a, b = outs["1"].double(), outs["0"].double()
     assert float((a - b).norm() / b.norm()) < 1e-6
+
+
+@pytest.mark.parametrize("pn", [64, 128, 200, 256])
+def test_direct_solver_tensor_core_path(L, dev, pn):
+    """f2: the tcgen05 3xTF32 form of the direct solver (csrc/direct_tc.cu, default for pn >= 64) against the FP32
+    CUDA-core kernels (LITHO_DIRECT_TC=0) and a float64 evaluation of the same operator, with weights, a shifted
+    source whose rolled pupil wraps around the grid, and a grid that is not a multiple of the 128-row tile."""
+    import ctypes as C
+    import os
+    from lithographysimulator_b200 import direct as D
+    from lithographysimulator_b200.imaging import AbbeEngine, source_shifts
+    eng = AbbeEngine.get(dev)
+    geom = torch.from_numpy(wl.manhattan(pn, seed=7 + pn))
+    mask = L.Mask(geom, 25, dev)
+    mft = mask.fraunhofer(193.0, False)
+    src = L.LightSource(0.5, 0.95, pn, 0.7, 0.2, -0.1, dev)           # shifted: some source points wrap the window
+    stride = max(1, pn // 16)
+    ls = src.generateQuasar(4, 0.3) * torch.from_numpy(wl.lattice(pn, stride)).to(dev)
+    ab = torch.tensor([0, 0, 0.02, 0, 60, 0.01], dtype=torch.float16, device=dev)
+    pf = L.Pupil(pn, 193.0, 0.7, ab, dev).generatePupilFunction()
+    n = int((ls != 0).sum())
+    assert n >= 8
+    w = torch.linspace(0.5, 2.0, n, device=dev)
+    outs = {}
+    for tc in ("1", "0"):
+        os.environ["LITHO_DIRECT_TC"] = tc
+        try:
+            outs[tc] = D.direct_abbe_image(mft, pf, ls, 25, 193.0, dev, weights=w, batch=5).double()
+            torch.cuda.synchronize(dev)
+        finally:
+            os.environ.pop("LITHO_DIRECT_TC", None)
+    st = C.c_int(0)
+    eng.lib.check(eng.lib.litho_direct_status(C.byref(st), 0), "litho_direct_status")
+    assert st.value == 0
+    # float64 evaluation of E = A G A^T with the library's own operator
+    A = D._operator(eng.lib, pn, 25, 193.0, -1, dev).to(torch.complex128)
+    sh = source_shifts(ls, pn).cpu().numpy()
+    ref = torch.zeros((pn, pn), dtype=torch.float64, device=dev)
+    for (d0, d1), wi in zip(sh, w.cpu().numpy()):
+        G = (torch.roll(pf, (int(d0), int(d1)), (0, 1)) * mft).to(torch.complex128)
+        E = A @ G @ A.T
+        ref += float(wi) * (E.real ** 2 + E.imag ** 2)
+    for tc in ("1", "0"):
+        err = float((outs[tc] - ref).norm() / ref.norm())
+        assert err < 1e-5, (tc, err)
+    assert float((outs["1"] - outs["0"]).norm() / outs["0"].norm()) < 1e-5
