@@ -171,12 +171,14 @@ int litho_mask_spectrum(const int16_t* geometry, int pn, double eps, int N, void
  * litho_direct_operator builds A[a][c] = w[c] * exp(sign*i*(2*pi/lambda)*fp16(fp16(k[a])*fp16(x[c])))
  * (pn x pn complex64): sign = -1 for imaging (imageformation.py:52), +1 for the mask spectrum (mask.py:42). */
 int litho_direct_operator(int pn, double pixelSize, double wavelength, int sign, void* A, void* stream);
+/* source points per launch group used when batch <= 0 (FP32 kernels: 8; tensor-core kernels: enough to fill the SMs) */
+int litho_direct_default_batch(int pn, const int* bbox);
 size_t litho_direct_workspace_bytes(int pn, const int* bbox, int batch);
 /* abbeImage(fft=False) hot loop                                 imageformation.py:59-65 with :3-30
  *   intensity[pn][pn] += sum_s w_s | A (roll(pupil, shift_s) * maskFT) A^T |^2   (natural row-major order)
  * pn >= 64: both products run on the tensor cores (tcgen05.mma kind::tf32, 3xTF32 hi/lo split, fp32 accumulation in
  * tensor memory; measured 1e-6 rel-L2 against float64) -- LITHO_DIRECT_TC=0 selects the FP32 CUDA-core kernels,
- * which also serve smaller grids.  batch <= 0: 8 source points per launch group. */
+ * which also serve smaller grids.  batch <= 0: litho_direct_default_batch source points per launch group. */
 int litho_direct_accumulate(const void* A, const void* maskFT, const void* pupil, int pn, const int* bbox,
                             const int32_t* shifts, const float* weights, int n_src, int batch, float* intensity,
                             void* workspace, size_t workspace_bytes, void* stream);

@@ -57,6 +57,7 @@ SYMBOLS = [
     ("litho_mask_spectrum_workspace_bytes", C.c_size_t, [C.c_int, C.c_double, C.c_int]),
     ("litho_mask_spectrum", C.c_int, [_P, C.c_int, C.c_double, C.c_int, _P, _P, C.c_size_t, _P]),
     ("litho_direct_operator", C.c_int, [C.c_int, C.c_double, C.c_double, C.c_int, _P, _P]),
+    ("litho_direct_default_batch", C.c_int, [C.c_int, C.POINTER(C.c_int)]),
     ("litho_direct_workspace_bytes", C.c_size_t, [C.c_int, C.POINTER(C.c_int), C.c_int]),
     ("litho_direct_accumulate", C.c_int, [_P, _P, _P, C.c_int, C.POINTER(C.c_int), _P, _P, C.c_int, C.c_int, _P, _P,
                                           C.c_size_t, _P]),

@@ -13,7 +13,7 @@
 //   * 3xTF32: x = hi + lo with hi = rna_tf32(x); D += A_hi B_hi + A_lo B_hi + A_hi B_lo.  One TF32 pass misses
 //     the 1e-5 parity bar by a factor of 20 (measured 2.2e-4, profiles/r03a_direct_bench.json), three passes keep
 //     it at 1e-6 -- the dropped lo*lo term and the TF32 truncation of lo are O(2^-21).
-// One CTA = one 128-row tile x one tile of <= 128 complex columns x one source point.  All 128 threads split the
+// One CTA = one 128-row tile x one tile of <= 128 complex columns x one source point.  All 256 threads split the
 // fp32 operands and write them to shared memory in the canonical K-major SWIZZLE_128B layout (32 tf32 = 128 bytes
 // per row and k-block), one thread issues the 12 MMAs of a k-block, tcgen05.commit releases the stage through an
 // mbarrier (2 stages: the fill of k-block j+1 overlaps the MMAs of k-block j), and the epilogue reads the
@@ -27,7 +27,7 @@ namespace litho_tc {
 
 constexpr int BM = 128;                 // rows per CTA = TMEM lanes
 constexpr int KB = 16;                  // complex K elements per k-block (32 tf32 = one 128-byte swizzle row)
-constexpr int THREADS = 128;
+constexpr int THREADS = 256;            // two threads per operand row (4 of its 8 chunks each); 8 warps in the epilogue
 constexpr int A_TILE = BM * 128;        // bytes of one A operand tile (hi or lo)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -83,10 +83,11 @@ __device__ __forceinline__ int imod(int a, int b) {
     return m < 0 ? m + b : m;
 }
 
-// grid = (M tiles, N tiles, source points of the batch), block = 128
+// grid = (M tiles, N tiles, source points of the batch), block = 256
 __global__ void __launch_bounds__(THREADS, 1) direct_tc_kernel(const __grid_constant__ TcParams P) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int row = tid & (BM - 1), half = tid >> 7;     // operand row of this thread, and which half of its chunks
     const int mt = blockIdx.x, nt = blockIdx.y, sl = blockIdx.z;
     const int pn = P.pn;
     const int NT = P.NT;                        // complex columns per N tile (multiple of 8, <= 128)
@@ -120,10 +121,10 @@ __global__ void __launch_bounds__(THREADS, 1) direct_tc_kernel(const __grid_cons
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NR >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
     // ---- this thread's rows of the two operands ----
-    const int m = mt * BM + tid;                 // A row (an output row of this stage)
+    const int m = mt * BM + row;                 // A row (an output row of this stage)
     const cplx2* Arow = P.A + (size_t)(m < pn ? m : 0) * pn;
-    const int n = nt * NT + tid;                 // Bt row (an output column of this stage), threads >= NT idle in the B fill
-    const bool n_fill = tid < NT;
+    const int n = nt * NT + row;                 // Bt row (an output column of this stage), rows >= NT idle in the B fill
+    const bool n_fill = row < NT;
     const bool n_live = n_fill && n < (P.stage == 1 ? P.Sr : pn);
     const cplx2* Urow = P.U + ((size_t)sl * pn + (n_live ? n : 0)) * P.Upitch;                    // stage 2
     const cplx2* prow = P.pupil + (size_t)(P.pr0 + (n_live ? n : 0)) * pn + P.pc0;                // stage 1
@@ -139,21 +140,23 @@ __global__ void __launch_bounds__(THREADS, 1) direct_tc_kernel(const __grid_cons
         unsigned char* b_lo = b_hi + b_tile;
         if (j >= 2 && !mbar_wait(smem_u32(bars + s), (uint32_t)(((j >> 1) - 1) & 1))) lost = true;   // MMAs of k-block j-2 done
         const int k0 = j * KB;
-        // A tile: row tid, 16 complex = 8 chunks of 2
+        // A tile: 16 complex per row = 8 chunks of 2, four per thread
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
+        for (int cc = 0; cc < 4; ++cc) {
+            const int c = 4 * half + cc;
             const int k = k0 + 2 * c;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (m < pn) {
                 if (k < Kc) { const cplx2 z = __ldg(Arow + imod(kbase + k, pn)); v.x = z.x; v.y = z.y; }
                 if (k + 1 < Kc) { const cplx2 z = __ldg(Arow + imod(kbase + k + 1, pn)); v.z = z.x; v.w = z.y; }
             }
-            st_pair(a_hi, a_lo, tid, c, v);
+            st_pair(a_hi, a_lo, row, c, v);
         }
-        // B tile: complex row n -> operand rows 2*tid (re, -im) and 2*tid+1 (im, re)
+        // B tile: complex row n -> operand rows 2*row (re, -im) and 2*row+1 (im, re)
         if (n_fill) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
+            for (int cc = 0; cc < 4; ++cc) {
+                const int c = 4 * half + cc;
                 cplx2 z[2];
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
@@ -168,8 +171,8 @@ __global__ void __launch_bounds__(THREADS, 1) direct_tc_kernel(const __grid_cons
                         }
                     }
                 }
-                st_pair(b_hi, b_lo, 2 * tid, c, make_float4(z[0].x, -z[0].y, z[1].x, -z[1].y));
-                st_pair(b_hi, b_lo, 2 * tid + 1, c, make_float4(z[0].y, z[0].x, z[1].y, z[1].x));
+                st_pair(b_hi, b_lo, 2 * row, c, make_float4(z[0].x, -z[0].y, z[1].x, -z[1].y));
+                st_pair(b_hi, b_lo, 2 * row + 1, c, make_float4(z[0].y, z[0].x, z[1].y, z[1].x));
             }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
@@ -193,9 +196,10 @@ __global__ void __launch_bounds__(THREADS, 1) direct_tc_kernel(const __grid_cons
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (lost && P.err) *P.err = 1;
 
-    // ---- epilogue: warp w owns lanes 32w .. 32w+31, thread = one output row ----
-    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
-    for (int c0 = 0; c0 < NR; c0 += 32) {       // 32 accumulator columns = 16 complex outputs
+    // ---- epilogue: a warp can reach the TMEM lanes 32*(warp % 4) .. +31; thread = one output row; warps 0-3 take
+    // the even 32-column chunks, warps 4-7 the odd ones ----
+    const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    for (int c0 = 32 * half; c0 < NR; c0 += 64) {       // 32 accumulator columns = 16 complex outputs
         uint32_t r[32];
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -208,18 +212,22 @@ __global__ void __launch_bounds__(THREADS, 1) direct_tc_kernel(const __grid_cons
             : "r"(taddr + (uint32_t)c0));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (m < pn) {
-            const int nbase = nt * NT + (c0 >> 1);
+            const int nloc = c0 >> 1;            // first complex column of this chunk inside the tile
+            const int nbase = nt * NT + nloc;
+            // the last chunk of a tile narrower than a multiple of 16 columns reads past NR: those columns belong
+            // to the next tile (another CTA), never store them
+            const int lim = (NT - nloc) < 16 ? (NT - nloc) : 16;
             if (P.stage == 1) {
                 cplx2* dst = P.Uout + ((size_t)sl * pn + m) * P.Upitch + nbase;
 #pragma unroll
                 for (int e = 0; e < 16; ++e)
-                    if (nbase + e < P.Sr) dst[e] = make_float2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1]));
+                    if (e < lim && nbase + e < P.Sr) dst[e] = make_float2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1]));
             } else {
                 float* dst = P.part + ((size_t)sl * pn + m) * pn + nbase;
 #pragma unroll
                 for (int e = 0; e < 16; ++e) {
                     const float x = __uint_as_float(r[2 * e]), y = __uint_as_float(r[2 * e + 1]);
-                    if (nbase + e < pn) dst[e] = x * x + y * y;
+                    if (e < lim && nbase + e < pn) dst[e] = x * x + y * y;
                 }
             }
         }
@@ -246,6 +254,11 @@ int tc_tile_cols(int n) {   // complex columns per N tile: <= 128, a multiple of
     const int tiles = (n + 127) / 128;
     const int per = (n + tiles - 1) / tiles;
     return (per + 7) / 8 * 8;
+}
+
+int tc_ctas_per_point(int pn, int n_out) {
+    const int nt = tc_tile_cols(n_out);
+    return ((pn + BM - 1) / BM) * ((n_out + nt - 1) / nt);
 }
 
 int tc_launch(TcParams P, int n_out, int batch, cudaStream_t st) {

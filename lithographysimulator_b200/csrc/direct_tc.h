@@ -25,6 +25,7 @@ struct TcParams {
     int* err;              // device word set to 1 if an mbarrier wait timed out (results invalid)
 };
 
+int tc_ctas_per_point(int pn, int n_out);   // CTAs one source point occupies in the stage with n_out output columns
 int tc_launch(TcParams P, int n_out, int batch, cudaStream_t st);
 int tc_reduce(const float* part, const float* weights, int s_begin, int batch, int pn, float* intensity, cudaStream_t st);
 

@@ -1583,9 +1583,29 @@ static bool direct_tc_enabled(int pn) {
 }
 static int tc_upitch(int Sr) { return (Sr + 15) / 16 * 16; }
 
+// Source points per launch group when the caller passes batch <= 0.  FP32 kernels: 8.  Tensor-core kernels: one CTA
+// covers a 128-row x <=128-column tile of ONE source point, so enough points to put two CTAs on every SM (capped at
+// 128 points: the workspace holds U and |E|^2 per point).
+int litho_direct_default_batch(int pn, const int* bbox) {
+    int Sr, Sc;
+    if (direct_check(pn, bbox, &Sr, &Sc)) return 0;
+#if !defined(LITHO_EMU)
+    if (direct_tc_enabled(pn)) {
+        int sms = 148, dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int per_point = litho_tc::tc_ctas_per_point(pn, Sr);    // stage 1 has the fewer CTAs per point
+        int b = (2 * sms + per_point - 1) / per_point;
+        return b < 8 ? 8 : (b > 128 ? 128 : b);
+    }
+#endif
+    return 8;
+}
+
 size_t litho_direct_workspace_bytes(int pn, const int* bbox, int batch) {
     int Sr, Sc;
-    if (direct_check(pn, bbox, &Sr, &Sc) || batch < 1) return 0;
+    if (direct_check(pn, bbox, &Sr, &Sc)) return 0;
+    if (batch < 1) batch = litho_direct_default_batch(pn, bbox);
+    if (batch < 1) return 0;
     const size_t fp32 = (size_t)batch * Sr * pn * sizeof(cplx);
     const size_t tc = (size_t)batch * pn * tc_upitch(Sr) * sizeof(cplx) + (size_t)batch * pn * pn * sizeof(float);
     return (direct_tc_enabled(pn) && tc > fp32) ? tc : fp32;
@@ -1665,7 +1685,7 @@ int litho_direct_accumulate(const void* A, const void* maskFT, const void* pupil
     if (n_src < 0) return fail(LITHO_ERR_ARG, "direct_accumulate: negative n_src");
     if (n_src == 0) return LITHO_OK;
     if (!shifts) return fail(LITHO_ERR_ARG, "direct_accumulate: shifts is null");
-    if (batch < 1) batch = 8;
+    if (batch < 1) batch = litho_direct_default_batch(pn, bbox);
     if (batch > n_src) batch = n_src;
     if (!workspace || workspace_bytes < litho_direct_workspace_bytes(pn, bbox, batch))
         return fail(LITHO_ERR_WORKSPACE, "direct_accumulate: workspace too small");

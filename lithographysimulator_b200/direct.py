@@ -24,7 +24,7 @@ def _bbox_arg(bbox):
     return (C.c_int * 4)(*bbox)
 
 
-def direct_abbe_image(maskFT, pupilF, lightsource, pixelSize, wavelength, dev, weights=None, batch: int = 8):
+def direct_abbe_image(maskFT, pupilF, lightsource, pixelSize, wavelength, dev, weights=None, batch: int = 0):
     """abbeImage(fft=False): sum over source points of |A (roll(P) * M) A^T|^2, no post-processing
     (reference imageformation.py:59-65, :77)."""
     eng = AbbeEngine.get(dev)
@@ -44,11 +44,15 @@ def direct_abbe_image(maskFT, pupilF, lightsource, pixelSize, wavelength, dev, w
         if bbox[1] < bbox[0]:
             return out
         A = _operator(lib, pn, pixelSize, wavelength, -1, dev)
-        batch = max(1, min(batch, n_src))
         box = _bbox_arg(bbox)
+        if batch <= 0:      # FP32 kernels: 8; tensor-core kernels: enough source points per launch to fill the SMs
+            batch = int(lib.litho_direct_default_batch(pn, box))
+        batch = max(1, min(batch, n_src))
         nbytes = int(lib.litho_direct_workspace_bytes(pn, box, batch))
         ws = eng.workspace(nbytes)
         w_d = None if weights is None else weights.to(device=dev, dtype=torch.float32).contiguous()
+        if w_d is not None and int(w_d.numel()) != n_src:
+            raise _native.LithoError(f"{int(w_d.numel())} weights for {n_src} source points")
         lib.check(lib.litho_direct_accumulate(A.data_ptr(), maskFT_d.data_ptr(), pupil_d.data_ptr(), pn, box,
                                               shifts.data_ptr(), None if w_d is None else w_d.data_ptr(), n_src, batch,
                                               out.data_ptr(), ws.data_ptr(), nbytes, eng.stream()),
