@@ -64,8 +64,9 @@ __device__ __forceinline__ void st_pair(unsigned char* hi_tile, unsigned char* l
     const uint32_t h0 = tf32_hi(v.x), h1 = tf32_hi(v.y), h2 = tf32_hi(v.z), h3 = tf32_hi(v.w);
     const uint32_t o = swz(row, c16);
     *reinterpret_cast<uint4*>(hi_tile + o) = make_uint4(h0, h1, h2, h3);
-    *reinterpret_cast<float4*>(lo_tile + o) = make_float4(v.x - __uint_as_float(h0), v.y - __uint_as_float(h1),
-                                                          v.z - __uint_as_float(h2), v.w - __uint_as_float(h3));
+    // the MMA truncates its 32-bit operands to TF32: round lo to nearest here, so that what is dropped is unbiased
+    *reinterpret_cast<uint4*>(lo_tile + o) = make_uint4(tf32_hi(v.x - __uint_as_float(h0)), tf32_hi(v.y - __uint_as_float(h1)),
+                                                        tf32_hi(v.z - __uint_as_float(h2)), tf32_hi(v.w - __uint_as_float(h3)));
 }
 
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
