@@ -330,7 +330,7 @@ def run_ours(args):
     support = eng.pupil_support(pf_d)
     # one plan for all ranks, chosen from ALL source points (the partial planes are summed)
     plan = eng.plan(pn, N, support, generic=True) if args.generic else eng.plan_for(pn, N, support, shifts_all)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    flush = torch.empty(160 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     # Pipelined, sharded imager (lithographysimulator_b200.distributed.ShardedPipeline): image i is accumulated by
     # all ranks together; rank i mod N sums the partial planes -- over peer memory (NVLink loads, litho_peer_sum)
@@ -566,18 +566,25 @@ def run_ours(args):
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         step_ach = algorithmic_flops(pn, N, n_src)["total"] / (ms_per_step * 1e-3) / 1e12
         # DRAM bytes per launch of the dominant kernel from the committed ncu capture (scaled by batch)
-        traffic, traffic_src = None, None
+        traffic, traffic_src, dram_per_image = None, None, None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
             if tj.get("config") == cfg.name and plan.path == 2:
                 traffic = (tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]) * batch / tj["batch"]
                 traffic_src = tj["source"]
+                rk = tj.get("rows_kernel")
+                if rk:   # both hot kernels, scaled from the captured batch to the whole image's source points
+                    per_pt = (tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"] +
+                              rk["dram_bytes_read_per_launch"] + rk["dram_bytes_write_per_launch"]) / tj["batch"]
+                    dram_per_image = per_pt * n_src
         except Exception:
             pass
         roofline = {
-            "bound": "fp32", "kernel": ("abbe_fast_cols_kernel" if plan.path == 2 else "abbe_cols_kernel") +
+            "bound": "fp32", "kernel": (("abbe_fast_cols_tma_kernel" if plan.column_tile() > 0 else "abbe_fast_cols_kernel")
+                                        if plan.path == 2 else "abbe_cols_kernel") +
                       " (column pass + |E|^2 accumulate)",
             "achieved": achieved, "peak": best, "unit": "TFLOP/s", "frac": achieved / best if best else None,
+            "frac_of_nominal_peak": achieved / peak_nominal,
             "peak_source": "FP32 FMA probe measured in this run (MEASURED_PEAKS.json has no FP32 entry); "
                            f"nominal {peak_nominal:.1f} TFLOP/s = SMs*128*2*max clock",
             "flops_per_launch": cols_flops, "ms_per_launch": cols_ms, "traffic": traffic,
@@ -586,8 +593,13 @@ def run_ours(args):
                             (kern["rows"]["ms_total"] / kern["rows"]["launches"] * 1e-3) / 1e12,
                             "ms_per_launch": kern["rows"]["ms_total"] / kern["rows"]["launches"]},
             "whole_step": {"achieved": step_ach * 1.0, "frac": step_ach / best if best else None,
+                           "frac_of_nominal_peak": step_ach / peak_nominal,
                            "flops_per_image": algorithmic_flops(pn, N, n_src)["total"]},
             "hbm": {"compulsory_bytes_per_image": 8 * pn * pn * 2 + 8 * n_src + 4 * pn * pn,
+                    "dram_bytes_per_image_measured": dram_per_image,
+                    "dram_gbs_at_this_rate": (dram_per_image / (ms_per_step * 1e-3) / 1e9 / world) if dram_per_image else None,
+                    "dram_note": "ncu dram__bytes of the row + column pass (profiles/traffic.json) scaled to the image's "
+                                 "source points: the intermediate T (16.8 MB per source point) makes one HBM round trip",
                     "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
         }
         # rows + cols per batch, plus per image: rim sums and the 6 interpolation kernels (fast path) + resample
@@ -628,7 +640,7 @@ def run_ours(args):
                 "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "complex64", "data": "synthetic",
                 "config": {"workload": workload_string(cfg, n_src, N),
-                           "l2": "flushed (256 MB write) between images, inside the timed region", "batch": batch,
+                           "l2": "flushed (160 MB write > 126 MB L2) between images, inside the timed region", "batch": batch,
                            "pipeline": "sequential, all-reduce, every rank post-processes" if args.no_pipeline else
                            "post-processing of image i overlaps the accumulation of image i+1 (2 streams); with N>1 "
                            "rank i mod N sums the partial planes and alone post-processes image i",
