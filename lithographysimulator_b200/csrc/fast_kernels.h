@@ -227,7 +227,7 @@ LITHO_HD void fast_row_load(cplx (&v)[PPT], const FastRowsParams& P, int s, int 
 }
 
 // Inputs of one column FFT: T[u][kc] for the thread's slots u = g + TG*e (column kc = src offset).
-// CG selects L2-coherent loads (T written by other CTAs of the same launch, fused kernel).
+// CG selects L2-coherent loads (T written by other CTAs of the same launch).
 template <int M, int PPT, bool CG>
 LITHO_HD void fast_col_load_raw(cplx (&v)[PPT], const cplx* src, int Sr, int g) {
     using F = FastShape<M, PPT>;
@@ -550,162 +550,6 @@ LITHO_HD void fast_cols_tma_body(const FastColsParams& P, const Ctx& ctx, unsign
     }
 #pragma unroll
     for (int e = 0; e < PPT; ++e) dst[(size_t)(TG * e) * M] = acc[e];
-}
-
-// ----------------------------------------------------------------------------- fused persistent kernel
-// One launch per image: persistent CTAs pull work items from a global queue that interleaves the row
-// pass of source-point group k+1 with the column pass of group k.  T lives in a small ring of slots that
-// stays L2-resident (no HBM round trip, no launch gaps, no partial waves except at the very end, twiddle
-// tables loaded once per CTA).  Dependencies are device-scope counters:
-//   rows_done[k]  : column items of group k wait until every row item of group k has been stored;
-//   cols_done[k]  : row items of group k+NS wait until the ring slot has been consumed;
-//   tile_ver[t]   : the read-modify-write of an intensity tile is ordered across groups (deterministic sums).
-// Every item only waits on items that precede it in the queue, and items are handed out in queue order
-// to running CTAs, so the scheme cannot deadlock whatever the number of resident CTAs.
-struct FusedParams {
-    FastRowsParams r;      // pupil, mask, window, shifts, tables; r.T = ring base
-    const float* weights;
-    float* ic;
-    int n_src, B, NS;      // source points, points per group, ring slots (in groups)
-    int G, nRf, nRl, nC;   // groups, row items of a full / the last group, column items per group
-    int* ctr;              // [0] next item, [1..G] rows_done, [1+G..2G] cols_done, [1+2G..] tile_ver[nC]
-    int* err;              // set to 1 if a wait timed out (results are then invalid)
-};
-
-template <class Ctx>
-LITHO_HD void fused_wait(const int* p, int target, int* err, const Ctx& ctx) {
-    if (ctx.tid() == 0) {
-        long spins = 0;
-        while (ld_volatile_i(p) < target) {
-            backoff();
-            if (++spins > 20000000L) {  // ~4 s: never hang the GPU on a logic error
-                *err = 1;
-                break;
-            }
-        }
-        fence_gpu();
-    }
-    ctx.sync();
-}
-
-template <int M, class Ctx>
-LITHO_HD void fast_fused_body(const FusedParams& P, const Ctx& ctx, cplx* smem, int* s_item) {
-    constexpr int PPT = 32;
-    using F = FastShape<M, PPT>;
-    using Sh = typename F::Sh;
-    constexpr int TG = F::TG;
-    constexpr int CB = F::CB;
-    static_assert(F::ROW_THREADS == 256, "fused kernel needs 256-thread row shape");
-    if constexpr (F::COL_THREADS != 256) return;  // experimental column shapes: fused kernel unavailable
-    constexpr int NBLK = M / CB;
-    cplx* tab = smem;
-    fast_load_tables<M, PPT>(P.r.tables, tab, ctx);
-    cplx* exbase = smem + F::NTAB_PAD;
-    const SmemTw<M, PPT> tw{tab};
-    const int tid = ctx.tid();
-    // row-role indices
-    const int grp = tid / TG, gr = tid - grp * TG;
-    // column-role indices
-    const int col = tid % CB, gc = tid / CB;
-    int* rows_done = P.ctr + 1;
-    int* cols_done = P.ctr + 1 + P.G;
-    int* tile_ver = P.ctr + 1 + 2 * P.G;
-    const size_t slot_elems = (size_t)P.B * 2 * P.r.Sr * M;
-    const int nfull = P.G >= 2 ? P.G - 2 : 0;       // blocks [R(k+1) full, C(k)]
-    const int bs = P.nRf + P.nC;
-    const int nR0 = P.G >= 2 ? P.nRf : P.nRl;
-    const long total = (long)nR0 + (long)nfull * bs + (P.G >= 2 ? (long)P.nRl + P.nC : 0) + P.nC;
-
-    for (;;) {
-        if (tid == 0) *s_item = atomic_add_i(P.ctr, 1);
-        ctx.sync();
-        long i = *s_item;
-        ctx.sync();
-        if (i >= total) break;
-        // ---- decode queue position -> (is_row, group k, index within the pass) ----
-        bool is_row;
-        int k, idx;
-        if (i < nR0) { is_row = true; k = 0; idx = (int)i; }
-        else {
-            i -= nR0;
-            if (i < (long)nfull * bs) {
-                k = (int)(i / bs);
-                const int o = (int)(i - (long)k * bs);
-                if (o < P.nRf) { is_row = true; k += 1; idx = o; }
-                else { is_row = false; idx = o - P.nRf; }
-            } else {
-                i -= (long)nfull * bs;
-                if (P.G >= 2 && i < P.nRl) { is_row = true; k = P.G - 1; idx = (int)i; }
-                else {
-                    if (P.G >= 2) i -= P.nRl;
-                    is_row = false;
-                    if (P.G >= 2 && i < P.nC) { k = P.G - 2; idx = (int)i; }
-                    else { k = P.G - 1; idx = (int)(P.G >= 2 ? i - P.nC : i); }
-                }
-            }
-        }
-        const int s0 = k * P.B;
-        const int Bk = (P.n_src - s0) < P.B ? (P.n_src - s0) : P.B;
-        cplx* Tslot = P.r.T + (size_t)(k % P.NS) * slot_elems;
-
-        if (is_row) {
-            if (k >= P.NS) fused_wait(cols_done + (k - P.NS), P.nC, P.err, ctx);  // ring slot consumed
-            const int item = idx * F::ROW_GROUPS + grp;
-            const bool active = item < Bk * P.r.Sr * 2;
-            const int r = item & 1;
-            const int li = item >> 1;
-            const int sl = active ? li / P.r.Sr : 0;
-            const int line = active ? li - sl * P.r.Sr : 0;
-            cplx v[PPT];
-            if (active) {
-                fast_row_load<M, PPT>(v, P.r, s0 + sl, line, r, gr, tab);
-            } else {
-#pragma unroll
-                for (int e = 0; e < PPT; ++e) v[e] = mk(0.f, 0.f);
-            }
-            const GroupSync<Ctx, F::ROW_SYNC> gs{ctx, 1 + grp, TG};
-            fft_run<M, PPT, false>(v, exbase + grp * Sh::SMEM_ELEMS, 1, gr, tw, gs);
-            if (active) {
-                cplx* dst = Tslot + ((size_t)(sl * 2 + r) * P.r.Sr + line) * M + gr;
-#pragma unroll
-                for (int e = 0; e < PPT; ++e) dst[TG * e] = v[e];
-            }
-            ctx.sync();
-            if (tid == 0) {
-                fence_gpu();
-                atomic_add_i(rows_done + k, 1);
-            }
-        } else {
-            const int nRk = (k == P.G - 1) ? P.nRl : P.nRf;
-            fused_wait(rows_done + k, nRk, P.err, ctx);   // every row of this group is in T
-            fused_wait(tile_ver + idx, k, P.err, ctx);    // previous groups have updated this tile
-            const int rr = idx / (2 * NBLK);
-            const int rc = (idx / NBLK) & 1;
-            const int kc = (idx % NBLK) * CB + col;
-            const GroupSync<Ctx, 2> gs{ctx, 0, 0};
-            float* dst = P.ic + ((size_t)(rr * 2 + rc) * M + gc) * M + kc;
-            float acc[PPT];
-#pragma unroll
-            for (int e = 0; e < PPT; ++e) acc[e] = ldcg_f(dst + (size_t)(TG * e) * M);
-            for (int sl = 0; sl < Bk; ++sl) {
-                const cplx* src = Tslot + ((size_t)(sl * 2 + rc) * P.r.Sr) * M + kc;
-                cplx v[PPT];
-                fast_col_load<M, PPT, true>(v, src, P.r.Sr, rr, gc, tab);
-                fft_run<M, PPT, false>(v, exbase + col, CB, gc, tw, gs);
-                const float w = P.weights ? P.weights[s0 + sl] : 1.f;
-#pragma unroll
-                for (int e = 0; e < PPT; ++e) acc[e] += w * cnorm2(v[e]);
-            }
-#pragma unroll
-            for (int e = 0; e < PPT; ++e) stcg_f(dst + (size_t)(TG * e) * M, acc[e]);
-            ctx.sync();
-            if (tid == 0) {
-                fence_gpu();
-                atomic_add_i(tile_ver + idx, 1);
-                atomic_add_i(cols_done + k, 1);
-            }
-        }
-    }
 }
 
 // ----------------------------------------------------------------------------- rim lines

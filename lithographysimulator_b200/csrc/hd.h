@@ -88,7 +88,7 @@ LITHO_HD void stcg_f(float* p, float v) {
     *p = v;
 #endif
 }
-// device-scope counters used by the fused persistent kernel
+// device-scope counter helpers
 LITHO_HD int atomic_add_i(int* p, int v) {
 #if defined(__CUDA_ARCH__)
     return atomicAdd(p, v);

@@ -210,40 +210,6 @@ int fast_tma_cols_m(int which) {
     }
 }
 
-#if LITHO_INST_M >= 512 && LITHO_INST_M <= 2048
-template <int M>
-struct FusedSmem {
-    using F = FastShape<M, 32>;
-    static constexpr size_t EX = F::ROW_SMEM > F::COL_SMEM ? F::ROW_SMEM : F::COL_SMEM;
-    static constexpr size_t BYTES = EX + 16;  // + the broadcast slot of the work-queue index
-};
-#if !defined(LITHO_EMU)
-template <int M>
-__global__ void __launch_bounds__(256, 2) abbe_fast_fused_kernel(const __grid_constant__ FusedParams P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    int* s_item = reinterpret_cast<int*>(smem_raw + FusedSmem<M>::EX);
-    fast_fused_body<M>(P, DevCtx{}, reinterpret_cast<cplx*>(smem_raw), s_item);
-}
-#endif
-template <int M>
-int launch_fast_fused_m(const FusedParams& P, int gx, litho_stream_t st) {
-    if (FastShape<M, 32>::COL_THREADS != 256) return -2;  // the fused body needs 256-thread column tiles
-#if defined(LITHO_EMU)
-    (void)st;
-    litho_emu::launch(gx, 1, 1, 256, FusedSmem<M>::BYTES, [&](const litho_emu::EmuCtx& c, char* s) {
-        fast_fused_body<M>(P, c, (cplx*)s, (int*)(s + FusedSmem<M>::EX));
-    });
-    return 0;
-#else
-    int e = set_smem(abbe_fast_fused_kernel<M>, FusedSmem<M>::BYTES);
-    if (e) return e;
-    abbe_fast_fused_kernel<M><<<dim3(gx, 1, 1), dim3(256, 1, 1), FusedSmem<M>::BYTES, st>>>(P);
-    return (int)cudaGetLastError();
-#endif
-}
-template int launch_fast_fused_m<LITHO_INST_M>(const FusedParams&, int, litho_stream_t);
-#endif
-
 template int launch_fast_rows_m<LITHO_INST_M, 32>(const FastRowsParams&, int, litho_stream_t);
 template int launch_fast_cols_m<LITHO_INST_M, 32>(const FastColsParams&, litho_stream_t);
 template int fast_ntab_m<LITHO_INST_M, 32>();

@@ -36,9 +36,5 @@ template <int M, int PPT>
 int fast_ntab_m();
 template <int M, int PPT>
 int fast_tma_cols_m(int which);
-// fused persistent kernel (fast_fused_body), instantiated for M = 512, 1024, 2048
-template <int M>
-int launch_fast_fused_m(const FusedParams& P, int gx, litho_stream_t st);
-#define LITHO_FOR_EACH_FUSED_M(X) X(512) X(1024) X(2048)
 #define LITHO_FOR_EACH_FAST_M(X) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096)
 }  // namespace litho

@@ -392,10 +392,6 @@ struct litho_plan {
     mutable const void* last_ws;
     mutable int last_batch;
     mutable int cols_recorded[LITHO_TSLOTS];
-    int fused;       // 1: one persistent launch per accumulate call (fast_fused_body)
-    int fused_B;     // source points per group of the fused kernel
-    int* counters;   // device: work-queue index, dependency counters, error flag (owned by the plan)
-    int counters_cap;
     int* status;     // device, 4 ints: [0] a shift had to be clamped, [1] a TMA tile copy never completed
     float* rim_scratch;   // device: LITHO_RIM_CHUNKS private slices of the rim sums (deterministic two-stage sum)
     size_t rim_stride;    // floats per slice
@@ -427,14 +423,6 @@ static int dispatch_fast_cols(int M, int ppt, const FastColsParams& P, litho_str
 #define X(m) case m: return launch_fast_cols_m<m, 32>(P, st);
 #endif
         LITHO_FOR_EACH_FAST_M(X)
-#undef X
-    }
-    return -1;
-}
-static int dispatch_fast_fused(int M, const FusedParams& P, int gx, litho_stream_t st) {
-    switch (M) {
-#define X(m) case m: return launch_fast_fused_m<m>(P, gx, st);
-        LITHO_FOR_EACH_FUSED_M(X)
 #undef X
     }
     return -1;
@@ -672,7 +660,7 @@ int litho_plan_create_lines(int pn, int N, const int* bbox, int lines, int flags
     size_t per = (size_t)p->zp.R * p->Sr * p->zp.Wr * sizeof(cplx);
     // ---- fast path eligibility: even window fit S <= Mf+1, coarse grid Nc = 2*Mf no finer than N ----
     p->path = 1; p->tables = nullptr; p->tables_c = nullptr; p->tma_box_rows = 0; p->Mf = p->Nc = p->q = 0; p->er = p->ec = -1;
-    p->fused = 0; p->fused_B = 2; p->counters = nullptr; p->counters_cap = 0; p->tma_cols = 0;
+    p->tma_cols = 0;
     p->status = nullptr; p->rim_scratch = nullptr; p->rim_stride = 0;
     p->last_ws = nullptr; p->last_batch = 0;
     for (int i = 0; i < LITHO_TSLOTS; ++i) p->cols_recorded[i] = 0;
@@ -732,23 +720,6 @@ int litho_plan_create_lines(int pn, int N, const int* bbox, int lines, int flags
             }
         }
 #endif
-        // fused persistent kernel: available for 512 <= M <= 2048 with 32 points per thread
-        // (measured slower than the two-kernel pipeline at cfg3, profiles/README.md: off unless LITHO_FUSED=1)
-        p->fused = 0;
-        if (const char* env = getenv("LITHO_FUSED")) p->fused = (atoi(env) != 0 && p->ppt == 32 && Mf >= 512 && Mf <= 2048);
-        if (const char* env = getenv("LITHO_FUSED_B")) {
-            const int v = atoi(env);
-            if (v >= 1 && v <= 16) p->fused_B = v;
-        }
-        if (p->fused) {
-            p->counters_cap = 1 + 2 * 65536 + 4 * Mf + 8;
-            rc = be_malloc((void**)&p->counters, sizeof(int) * p->counters_cap);
-            if (rc != 0) {
-                be_free(p->tables);
-                delete p;
-                return fail(LITHO_ERR_CUDA, std::string("plan_create: counters: ") + be_errstr(rc));
-            }
-        }
         p->path = 2; p->Mf = Mf; p->Nc = 2 * Mf; p->q = N / (2 * Mf);
         // TMA-staged column kernel where the shape has one (32 <= M <= 4096).  LITHO_TMA=0 selects plain loads,
         // LITHO_COL_NARROW=0/1 the wide (one 512-thread CTA per SM) or narrow (two 256-thread CTAs) tile.
@@ -840,7 +811,6 @@ void litho_plan_destroy(litho_plan_t* p) {
     if (!p) return;
     if (p->tables) be_free(p->tables);
     if (p->tables_c) be_free(p->tables_c);
-    if (p->counters) be_free(p->counters);
     if (p->status) be_free(p->status);
     if (p->rim_scratch) be_free(p->rim_scratch);
 #if !defined(LITHO_EMU)
@@ -1068,44 +1038,7 @@ static int accumulate_impl(const litho_plan_t* p, const void* maskFT, const void
         memset(&fc, 0, sizeof(fc));
         fc.T = (const cplx*)workspace; fc.Sr = p->Sr; fc.weights = weights; fc.tables = p->tables;
         fc.ic = intensity; fc.status = p->status;
-        const bool use_fused = p->fused && nf == 1 && (phases & 3) == 3 &&
-                               workspace_bytes >= 2 * (size_t)p->fused_B * 2 * p->Sr * p->Mf * sizeof(cplx);
-        if (use_fused) {
-            // one persistent launch per chunk of <= 65536 groups (counter capacity)
-            const int B = p->fused_B;
-            const size_t group_bytes = (size_t)B * 2 * p->Sr * p->Mf * sizeof(cplx);
-            int NS = (int)(workspace_bytes / group_bytes);
-            if (NS > 4) NS = 4;  // keep the ring L2-resident
-            if (NS < 2) NS = 0;
-            const int nC = 4 * (p->Mf / (256 / (p->Mf / 32)));
-            for (int s0 = 0; s0 < n_src; s0 += 65536 * B) {
-                const int ns = (n_src - s0) < 65536 * B ? (n_src - s0) : 65536 * B;
-                FusedParams fp;
-                memset(&fp, 0, sizeof(fp));
-                fp.r = fr;
-                fp.r.shifts = (const int2_*)shifts + s0;
-                fp.weights = weights ? weights + s0 : nullptr;
-                fp.ic = intensity;
-                fp.n_src = ns; fp.B = B; fp.NS = NS;
-                fp.G = (ns + B - 1) / B;
-                const int Bl = ns - (fp.G - 1) * B;
-                const int groups_per_item = 256 / (p->Mf / 32);
-                fp.nRf = (B * p->Sr * 2 + groups_per_item - 1) / groups_per_item;
-                fp.nRl = (Bl * p->Sr * 2 + groups_per_item - 1) / groups_per_item;
-                fp.nC = nC;
-                const int n_ctr = 1 + 2 * fp.G + nC;
-                fp.ctr = p->counters;
-                fp.err = p->counters + p->counters_cap - 1;
-#if defined(LITHO_EMU)
-                memset(p->counters, 0, sizeof(int) * n_ctr);
-#else
-                BE_CHECK((int)cudaMemsetAsync(p->counters, 0, sizeof(int) * n_ctr, st));
-#endif
-                const int frc = dispatch_fast_fused(p->Mf, fp, p->n_sm * 2, st);
-                if (frc == -2) return fail(LITHO_ERR_ARG, "accumulate: fused kernel not built for this column shape (unset LITHO_FUSED)");
-                BE_CHECK(frc);
-            }
-        } else {
+        {
         // T is double-buffered: the row pass of batch b+1 runs on the plan's auxiliary stream while the
         // column pass of batch b runs on the caller's stream, so the tail of one kernel overlaps the head
         // of the other (both are short, ~20-40 us at cfg3).  rows(b) -> cols(b) and cols(b) -> rows(b+LITHO_TSLOTS)

@@ -176,31 +176,6 @@ def test_emu_fast_path_subfft_256():
     assert O.rel_l2(img, np.abs(e) ** 2) < H.TOL
 
 
-def test_emu_fused_persistent_kernel(monkeypatch):
-    """pn = 1024 -> sub-FFT 512: the fused persistent kernel (work queue interleaving the row pass of group
-    k+1 with the column pass of group k, ring of T slots, dependency counters).  Three groups of one source
-    point exercise every branch of the queue decoder; checked against the oracle."""
-    monkeypatch.setenv("LITHO_FUSED", "1")   # experimental path, off by default
-    monkeypatch.setenv("LITHO_FUSED_B", "1")
-    pn = 1024
-    pf, _ = O.pupil_function([0, 0, 0.01, 0, 40], pn, 0.7, 193.0)
-    rng = np.random.default_rng(11)
-    mft = (rng.standard_normal((pn, pn)) + 1j * rng.standard_normal((pn, pn))).astype(np.complex64)
-    shifts = np.array([[10, -20], [-100, 37], [250, 255]], np.int32)
-    w = np.array([1.0, 0.5, 2.0], np.float32)
-    try:
-        img, info = H.emu_abbe_fft(mft, pf, None, 25.0, 193.0, shifts=shifts, weights=w, postprocess=False)
-    except Exception as e:  # built with a column-tile shape the fused body does not support
-        if "fused kernel not built" in str(e):
-            pytest.skip(str(e))
-        raise
-    assert info["path"] == 2 and info["M"] == 512, info
-    ref = np.zeros((pn, pn))
-    for (d0, d1), wi in zip(shifts, w):
-        ref += wi * np.abs(O.calculate_fft_aerial(np.roll(pf, (d0, d1), (0, 1)), mft, pn, 2048)) ** 2
-    assert O.rel_l2(img, ref) < H.TOL
-
-
 def test_emu_complex_field():
     f = KAT["field_fft_64"]
     lib = H.emu_lib()
