@@ -393,3 +393,23 @@ def test_emu_status_word_reports_clamped_shift():
     assert plan.status() == (1, 0)
     assert plan.status() == (0, 0)
     plan.close()
+
+
+def test_emu_subfft_4096_multi_tile_tma_column_pass():
+    """Sub-FFT 4096 (the cfg5 kernel shape: radix 32 x 32 x 4, TMA-staged column pass whose exchange buffer, tile and
+    tables fill the 227 KB of the CTA, third-pass twiddles read from global memory) on a synthetic 2100-px grid with a
+    2060-px dense window, N = 8192, two source points in ONE batch -- the tile of point 1 is copied while the FFT of
+    point 0 uses the exchange buffer, so any overlap of the two regions shows.  Against the oracle."""
+    pn, win, ps = 2100, 2060, 12.37
+    rng = np.random.default_rng(5)
+    lo = pn // 2 - win // 2
+    pup = np.zeros((pn, pn), np.complex64)
+    pup[lo:lo + win, lo:lo + win] = rng.standard_normal((win, win)) + 1j * rng.standard_normal((win, win))
+    mft = (rng.standard_normal((pn, pn)) + 1j * rng.standard_normal((pn, pn))).astype(np.complex64)
+    shifts = np.array([[3, -5], [-7, 11]], np.int32)
+    img, info = H.emu_abbe_fft(mft, pup, None, ps, 193.0, shifts=shifts, postprocess=False, batch=2)
+    assert info["path"] == 2 and info["M"] == 4096 and info["N"] == 8192 and info["column_tile"] == 2, info
+    ref = np.zeros((pn, pn))
+    for d0, d1 in shifts:
+        ref += np.abs(O.calculate_fft_aerial(np.roll(pup, (int(d0), int(d1)), (0, 1)), mft, pn, 8192)) ** 2
+    assert O.rel_l2(img, ref) < H.TOL
