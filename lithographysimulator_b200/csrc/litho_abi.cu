@@ -802,6 +802,15 @@ int litho_plan_create_lines(int pn, int N, const int* bbox, int lines, int flags
     const size_t target = (p->path == 2) ? ((size_t)816 << 20) : ((size_t)64 << 20);
     int b = (int)(target / (per ? per : 1));
     const int cap = (p->path == 2) ? 48 : 16;
+    if (p->path == 2) {
+        // large grids: every column-pass launch re-reads and re-writes the intensity plane (268 MB at 8192 px), so a
+        // launch must cover enough source points to amortise it -- measured at cfg5 (profiles/README.md, r03n):
+        // 571 / 483 / 463 / 439 / 424 ms per image at batches of 3 / 6 / 8 / 12 / 16.  At least 16 points while the
+        // 3-slot ring stays below 16 GB.
+        int floor_b = 16;
+        while (floor_b > 1 && (size_t)LITHO_TSLOTS * floor_b * per > ((size_t)16 << 30)) floor_b >>= 1;
+        if (b < floor_b) b = floor_b;
+    }
     p->default_batch = b < 1 ? 1 : (b > cap ? cap : b);
     *out = p;
     return LITHO_OK;
