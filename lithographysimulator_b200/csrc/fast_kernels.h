@@ -55,7 +55,17 @@ struct FastShape {
     static constexpr int ROW_THREADS = TG <= 256 ? 256 : TG;
     static constexpr int ROW_GROUPS = ROW_THREADS / TG;
     static constexpr int ROW_SYNC = TG <= 32 ? 0 : (ROW_GROUPS > 1 ? 1 : 2);  // 0 warp, 1 named barrier, 2 CTA
-    static constexpr size_t ROW_SMEM = (size_t)(NTAB_PAD + ROW_GROUPS * Sh::SMEM_ELEMS) * sizeof(cplx);
+    // M >= 4096: the full tables (65 KB) + two exchange regions (68 KB) would leave one 256-thread CTA per SM.  The row
+    // pass then uses the compact device table of the TMA column kernel (TmaShape layout: pre[0..M/2] mirrored about
+    // M/2, tw1) in shared memory and reads the third-pass table tw2 from global memory through L1: 24 KB of tables,
+    // 92 KB per CTA, two CTAs per SM.
+    static constexpr bool ROW_COMPACT = (M >= 4096);
+    static constexpr int CPRE_N = M / 2 + 1;
+    static constexpr int CTW1_OFF = (CPRE_N + 1) & ~1;
+    static constexpr int CTW2_OFF = CTW1_OFF + (R1 - 1) * NS1;          // (global memory only)
+    static constexpr int CTAB_SMEM_PAD = (CTW2_OFF + 1) & ~1;
+    static constexpr int ROW_TAB_ELEMS = ROW_COMPACT ? CTAB_SMEM_PAD : NTAB_PAD;
+    static constexpr size_t ROW_SMEM = (size_t)(ROW_TAB_ELEMS + ROW_GROUPS * Sh::SMEM_ELEMS) * sizeof(cplx);
     // cols kernel: CB adjacent columns per CTA, column fastest in the thread index (256 threads per CTA
     // where possible; CB >= 4 keeps every global request at full 32-byte sectors)
 // threads per column-pass CTA: 512 (16 columns = full 128-byte lines at M = 1024) measured 3% faster
@@ -94,6 +104,38 @@ struct SmemTw {
     }
 };
 
+// Row-pass twiddles: full shared-memory tables, or (FastShape::ROW_COMPACT) compact shared-memory tables + tw2 from global
+template <int M, int PPT>
+struct RowTw {
+    const cplx* tab;
+    const cplx* gtab;
+    template <int PASS>
+    LITHO_HD cplx get(int t, int k) const {
+        using F = FastShape<M, PPT>;
+        if constexpr (!F::ROW_COMPACT) {
+            if constexpr (PASS == 1) return tab[F::TW1_OFF + (t - 1) * F::NS1 + k];
+            else return tab[F::TW2_OFF + (t - 1) * F::NS2 + k];
+        } else {
+            if constexpr (PASS == 1) return tab[F::CTW1_OFF + (t - 1) * F::NS1 + k];
+            else return ldg_c(gtab + F::CTW2_OFF + (t - 1) * F::NS2 + k);
+        }
+    }
+};
+
+// pre-twiddle w_2M^u of slot u = g + TG*e from the full table (pre[0..M]) or the compact one (pre[0..M/2], mirrored)
+template <int M, int PPT>
+LITHO_HD cplx row_pre(const cplx* tab, int g, int e) {
+    using F = FastShape<M, PPT>;
+    constexpr int TG = F::TG;
+    if constexpr (!F::ROW_COMPACT) {
+        return tab[F::PRE_OFF + g + TG * e];
+    } else {
+        if (TG * e + TG - 1 <= M / 2) return tab[g + TG * e];
+        const cplx t = tab[M - TG * e - g];     // u >= M/2 (M/2 is a multiple of TG): w^u = -conj(w^(M-u))
+        return mk(-t.x, t.y);
+    }
+}
+
 // MODE 0: warp barrier, 1: named barrier `id` over `n` threads, 2: CTA barrier
 template <class Ctx, int MODE>
 struct GroupSync {
@@ -114,6 +156,7 @@ struct FastRowsParams {
     const int2_* shifts;
     int s_begin, batch;
     const cplx* tables;
+    const cplx* tables_c;   // compact tables (TmaShape layout), used by the row pass when FastShape::ROW_COMPACT
     cplx* T;  // [n_focus][batch][2][Sr][M]
     int* status;  // plan-owned device words: [0] set to 1 when a shift had to be clamped (contract violated)
     // focus batching (BASELINE cfg5): n_focus pupil planes (pupil + f*pupil_stride) share the mask
@@ -222,7 +265,7 @@ LITHO_HD void fast_row_load(cplx (&v)[PPT], const FastRowsParams& P, int s, int 
     }
     if (r) {
 #pragma unroll
-        for (int e = 0; e < PPT; ++e) v[e] = cmul(v[e], tab[F::PRE_OFF + g + TG * e]);
+        for (int e = 0; e < PPT; ++e) v[e] = cmul(v[e], row_pre<M, PPT>(tab, g, e));
     }
 }
 
@@ -280,15 +323,20 @@ LITHO_HD void fast_rows_body(const FastRowsParams& P, const Ctx& ctx, cplx* smem
     using Sh = typename F::Sh;
     constexpr int TG = F::TG;
     cplx* tab = smem;
-    fast_load_tables<M, PPT>(P.tables, tab, ctx);
+    if constexpr (F::ROW_COMPACT) {
+        for (int i = ctx.tid(); i < F::CTAB_SMEM_PAD; i += ctx.bdim()) tab[i] = P.tables_c[i];
+        ctx.sync();
+    } else {
+        fast_load_tables<M, PPT>(P.tables, tab, ctx);
+    }
     const int grp = ctx.tid() / TG;
     const int g = ctx.tid() - grp * TG;
-    cplx* ex = smem + F::NTAB_PAD + grp * Sh::SMEM_ELEMS;
+    cplx* ex = smem + F::ROW_TAB_ELEMS + grp * Sh::SMEM_ELEMS;
     const int nf = P.n_focus > 1 ? P.n_focus : 1;
     const int total = P.batch * P.Sr * 2 * nf;
     const int stride = ctx.gdx() * F::ROW_GROUPS;
     const int rounds = (total + stride - 1) / stride;
-    const SmemTw<M, PPT> tw{tab};
+    const RowTw<M, PPT> tw{tab, P.tables_c};
     const GroupSync<Ctx, F::ROW_SYNC> gs{ctx, 1 + grp, TG};
 
     for (int it = 0; it < rounds; ++it) {

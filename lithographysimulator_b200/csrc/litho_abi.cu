@@ -735,7 +735,7 @@ int litho_plan_create_lines(int pn, int N, const int* bbox, int lines, int flags
                 if (atoi(env) == 0) p->tma_cols = 0;
             }
         }
-        if (p->tma_cols > 0) {
+        if (p->tma_cols > 0 || Mf >= 4096) {   // (Mf >= 4096: the row pass uses the compact tables too)
             // compact tables: pre[0..M/2] (padded to an even count), then tw1 and tw2 as in the full layout
             std::vector<cplx> tc(tab.begin(), tab.begin() + Mf / 2 + 1);
             if (tc.size() & 1) tc.push_back(mk(0.f, 0.f));
@@ -1041,7 +1041,8 @@ static int accumulate_impl(const litho_plan_t* p, const void* maskFT, const void
         memset(&fr, 0, sizeof(fr));
         fr.pupil = (const cplx*)pupil; fr.mask = (const cplx*)maskFT; fr.pn = p->pn;
         fr.pr0 = p->bbox[0]; fr.pc0 = p->bbox[2]; fr.Sr = p->Sr; fr.Sc = p->Sc;
-        fr.shifts = (const int2_*)shifts; fr.tables = p->tables; fr.T = (cplx*)workspace; fr.status = p->status;
+        fr.shifts = (const int2_*)shifts; fr.tables = p->tables; fr.tables_c = p->tables_c; fr.T = (cplx*)workspace;
+        fr.status = p->status;
         fr.n_focus = nf; fr.pupil_stride = pupil_stride;
         FastColsParams fc;
         memset(&fc, 0, sizeof(fc));
