@@ -46,7 +46,7 @@ def main():
     pupils = []
     for d in sweep:
         ab = list(cfg.aberrations)
-        ab[4] = d
+        ab[4] = d   # (wl.aberrations_of(cfg, i))
         pupils.append(L.Pupil(pn, cfg.wavelength, cfg.na, torch.tensor(ab, dtype=torch.float16, device=dev),
                               dev).generatePupilFunction())
     torch.cuda.synchronize(dev)
@@ -75,11 +75,20 @@ def main():
         w_pt = (S + pn) * 5 * N * math.log2(N) + 6 * S * S + 4 * pn * pn
         flops = w_pt * n_src * len(sweep)
         finite = all(bool(torch.isfinite(i).all()) for i in imgs)
+        parity = None
+        gpath = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", f"{cfg.name}.npz")
+        if os.path.exists(gpath) and cfg.defocus_sweep:      # the golden is the sweep's first focus value
+            z = np.load(gpath)
+            st = int(z["sample_stride"])
+            ref = torch.from_numpy(z["image_sample"]).to(dev).double()
+            parity = float((imgs[0][::st, ::st].double() - ref).norm() / ref.norm())
         print(json.dumps({"workload": f"{cfg.name}: {pn}^2 mask x {len(sweep)} defocus values x {n_src} source points",
                           "n_gpus": world, "seconds_per_sweep": sec, "images_per_s": len(sweep) / sec,
                           "algorithmic_tflops": flops / sec / 1e12, "images": len(imgs),
                           "image_side": int(imgs[0].shape[0]), "finite": finite,
-                          "sharding": "pupils (focus values) over ranks, no reduce; images all-gathered"}), flush=True)
+                          "rel_l2_focus0_vs_reference_golden": parity,
+                          "sharding": "pupils (focus values) over ranks, no reduce; a rank's focus values share one row "
+                                      "pass per batch of source points (focus batching); images all-gathered"}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
