@@ -515,11 +515,24 @@ def run_ours(args):
     shard = (rank, world) if world > 1 else None
     # N > 1: every rank uploads 1/N of each input tensor and the slices are all-gathered over NVLink on a
     # communicator of their own (so the gathers do not queue behind the intensity reduce)
-    upload_pg = dist.new_group(backend="nccl") if world > 1 and not args.full_upload else None
+    # ... or (default) pulled from the peers' staging buffers by the copy engines (distributed.PeerStaging): no NCCL
+    # kernels next to the persistent compute kernels
+    upload_pg, upload_peers = None, None
+    if world > 1 and args.upload == "peer":
+        from lithographysimulator_b200.distributed import PeerStaging
+
+        def exchange(obj):
+            out = [None] * world
+            dist.all_gather_object(out, obj)
+            return out
+        upload_peers = PeerStaging(eng.lib, AbbeEngine.peer_staging_bytes(pn, ls_p.dtype), rank, world, exchange)
+        torch.cuda.synchronize(dev)
+    elif world > 1 and args.upload == "nccl":
+        upload_pg = dist.new_group(backend="nccl")
 
     def prepare(i):
         return eng.prepare(mft_p, pf_p, ls_p, cfg.pixel_size, 4 / pn, cfg.wavelength, slot=i % 2, shard=shard,
-                           plan=plan, upload_group=upload_pg)
+                           plan=plan, upload_group=upload_pg, upload_peers=upload_peers)
 
     def e2e_loop(n):
         prep = prepare(0)
@@ -541,7 +554,7 @@ def run_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te.item())
     h2d = mft_p.numel() * 8 + pf_p.numel() * 8 + ls_p.numel() * 8   # whole job: the slices of all ranks add up to this
-    if world > 1 and upload_pg is None:
+    if world > 1 and upload_pg is None and upload_peers is None:
         h2d *= world                                                 # every rank pulls the full tensors
     d2h = out_p[0].numel() * 4
     # the image that came back over PCIe must be the image the resident-input path produced
@@ -656,7 +669,10 @@ def run_ours(args):
                         "steps": e2e_steps, "rel_l2_vs_resident_path": e2e_check,
                         "how": "pinned host tensors -> AbbeEngine.prepare() (H2D + source-point extraction on a copy "
                                "stream, one image ahead" + ("; each rank uploads 1/N of every tensor, slices all-gathered "
-                               "over NVLink" if upload_pg is not None else "") + ") -> accumulate -> reduce -> finalize "
+                               "over NVLink (NCCL)" if upload_pg is not None else "") + ("; each rank uploads 1/N of the "
+                               "input bytes, the other slices are pulled from the peers' CUDA-IPC-mapped staging buffers by "
+                               "the copy engines (litho_peer_copy)" if upload_peers is not None else "") +
+                               ") -> accumulate -> sum -> finalize "
                                "-> D2H on the post-processing stream; wall clock over the loop, max over ranks; "
                                "h2d_bytes_per_step is the whole job's"},
                 "roofline": roofline, "cpu_baseline": cpu, "library_baseline": library, "parity": parity,
@@ -681,7 +697,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-library-baseline", action="store_true")
     ap.add_argument("--generic", action="store_true", help="force the generic fine-grid kernels")
-    ap.add_argument("--full-upload", action="store_true", help="e2e, N>1: every rank uploads the full inputs over PCIe")
+    ap.add_argument("--upload", default="peer", choices=["peer", "nccl", "full"],
+                    help="e2e, N>1: each rank uploads 1/N of the inputs and the slices are exchanged by copy-engine "
+                         "peer copies (default) or an NCCL all-gather; full: every rank uploads everything over PCIe")
     ap.add_argument("--no-chain", action="store_true", help="row pass of image i+1 waits for image i's last column pass")
     ap.add_argument("--no-pipeline", action="store_true", help="finalize each image before starting the next")
     ap.add_argument("--trace", action="store_true", help="extra untimed loop with per-image CUDA events on every rank")

@@ -225,6 +225,9 @@ int litho_peer_close(void* ptr);
 int litho_peer_free(void* ptr);
 int litho_peer_signal(void* const* flags, int n, uint64_t value, void* stream);
 int litho_peer_wait(const void* flags, int n, uint64_t value, int* err, void* stream);
+/* dst <- src (either may be a mapped peer buffer), `bytes` bytes, by the copy engines (no kernel) after the work
+ * queued on `stream` */
+int litho_peer_copy(void* dst, const void* src, size_t bytes, void* stream);
 int litho_peer_sum(float* out, const float* const* planes, int n, uint64_t elems, const void* flags, uint64_t value,
                    int* err, void* stream);
 const char* litho_peer_last_error(void);

@@ -77,6 +77,7 @@ SYMBOLS = [
     ("litho_peer_free", C.c_int, [_P]),
     ("litho_peer_signal", C.c_int, [C.POINTER(_P), C.c_int, C.c_uint64, _P]),
     ("litho_peer_wait", C.c_int, [_P, C.c_int, C.c_uint64, _P, _P]),
+    ("litho_peer_copy", C.c_int, [_P, _P, C.c_size_t, _P]),
     ("litho_peer_sum", C.c_int, [_P, C.POINTER(_P), C.c_int, C.c_uint64, _P, C.c_uint64, _P, _P]),
     ("litho_peer_last_error", C.c_char_p, []),
 ]
@@ -131,6 +132,9 @@ class NativeLib:
 
     def peer_wait(self, flags_ptr: int, n: int, value: int, err_ptr=None, stream: int = 0):
         self.check_peer(self.litho_peer_wait(flags_ptr, n, value, err_ptr, stream), "litho_peer_wait")
+
+    def peer_copy(self, dst_ptr: int, src_ptr: int, nbytes: int, stream: int = 0):
+        self.check_peer(self.litho_peer_copy(dst_ptr, src_ptr, nbytes, stream), "litho_peer_copy")
 
     def peer_sum(self, out_ptr: int, plane_ptrs, elems: int, flags_ptr=None, value: int = 0, err_ptr=None, stream: int = 0):
         arr = (_P * len(plane_ptrs))(*plane_ptrs)

@@ -272,6 +272,19 @@ int litho_peer_wait(const void* flags, int n, uint64_t value, int* err, void* st
     return LITHO_OK;
 }
 
+int litho_peer_copy(void* dst, const void* src, size_t bytes, void* stream) {
+    if (!dst || !src) return pfail(LITHO_ERR_ARG, "peer_copy: null argument");
+    if (bytes == 0) return LITHO_OK;
+#if defined(LITHO_EMU)
+    (void)stream;
+    memcpy(dst, src, bytes);
+#else
+    // device-to-device over NVLink by the copy engines: no kernel, nothing competes with compute for SMs
+    PCHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+#endif
+    return LITHO_OK;
+}
+
 int litho_peer_sum(float* out, const float* const* planes, int n, uint64_t elems, const void* flags, uint64_t value,
                    int* err, void* stream) {
     if (!out || !planes || n < 1 || n > LITHO_MAX_PEERS) return pfail(LITHO_ERR_ARG, "peer_sum: bad argument");

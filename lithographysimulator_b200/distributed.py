@@ -10,23 +10,10 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
-from .imaging import AbbeEngine, _as_c64, _require_cuda, epsilon_n, source_shifts
+from .imaging import AbbeEngine, _as_c64, _require_cuda, epsilon_n, source_shifts, tensor_from_ptr
 
-__all__ = ["shard_shifts", "abbe_image_sharded", "focus_sweep_sharded", "PeerPlanes", "ShardedPipeline",
+__all__ = ["shard_shifts", "abbe_image_sharded", "focus_sweep_sharded", "PeerPlanes", "PeerStaging", "ShardedPipeline",
            "tensor_from_ptr"]
-
-
-class _DevPtr:
-    """Minimal __cuda_array_interface__ carrier so that torch can view memory this package allocated itself
-    (peer-mapped buffers come from cudaMalloc + CUDA IPC, not from torch's caching allocator)."""
-
-    def __init__(self, ptr: int, n: int, typestr: str):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
-
-
-def tensor_from_ptr(ptr: int, n: int, dev, dtype=torch.float32) -> torch.Tensor:
-    typestr = {torch.float32: "<f4", torch.int32: "<i4", torch.int64: "<i8"}[dtype]
-    return torch.as_tensor(_DevPtr(ptr, n, typestr), device=dev)
 
 
 class PeerPlanes:
@@ -85,6 +72,85 @@ class PeerPlanes:
 
     def wait_consumed(self, slot: int, seq: int, stream: int = 0):
         self.lib.peer_wait(self._consumed_ptr(self.rank, slot), 1, seq, self.err_ptr, stream)
+
+    def close(self):
+        for r, b in enumerate(self.bases):
+            if r != self.rank and b:
+                self.lib.check_peer(self.lib.litho_peer_close(b), "litho_peer_close")
+        if self.base:
+            self.lib.check_peer(self.lib.litho_peer_free(self.base), "litho_peer_free")
+        self.base, self.bases = 0, []
+
+
+class PeerStaging:
+    """Input staging when all N ranks of a box need the same host inputs (one image computed N-way): every rank
+    uploads 1/N of the bytes over its own PCIe link into its peer-mapped buffer and pulls the other slices from the
+    peers' buffers with copy-engine transfers over NVLink (litho_peer_copy: no kernel, so nothing competes with the
+    persistent compute kernels for SMs -- an NCCL all-gather of the slices does).  `slots` buffers of `nbytes` each;
+    per slot and use number `seq` = 1, 2, ...:
+        wait pulled[slot][*] >= seq-1 (every peer has copied my previous slice)  ->  H2D of my slice
+        -> ready[slot][me] = seq on every rank  ->  wait ready[slot][*] >= seq  ->  copy the other slices
+        -> pulled[slot][me] = seq on every rank.
+    Pointers are plain ints (the CPU emulation drives the same class in the gloo tests)."""
+
+    MAILBOX_BYTES = 4096
+
+    def __init__(self, lib, nbytes: int, rank: int, world: int, exchange, slots: int = 2):
+        from ._native import MAX_PEERS
+        if world > MAX_PEERS:
+            raise ValueError(f"PeerStaging supports at most {MAX_PEERS} ranks")
+        self.lib, self.rank, self.world, self.slots = lib, rank, world, slots
+        self.max_peers = MAX_PEERS
+        self.nbytes = int(nbytes)
+        self.chunk = (-(-self.nbytes // world) + 255) // 256 * 256          # slice size, 256-byte aligned
+        self.slot_bytes = self.chunk * world
+        self.total_bytes = slots * self.slot_bytes + self.MAILBOX_BYTES
+        self.base, handle = lib.peer_alloc(self.total_bytes)
+        handles = exchange(handle)
+        self.bases = [self.base if r == rank else lib.peer_open(handles[r]) for r in range(world)]
+        exchange(b"mapped")
+        self.uses = [0] * slots
+
+    def buffer_ptr(self, slot: int, r: int | None = None) -> int:
+        return self.bases[self.rank if r is None else r] + slot * self.slot_bytes
+
+    def _mail(self, r: int) -> int:
+        return self.bases[r] + self.slots * self.slot_bytes
+
+    def _ready_ptr(self, owner: int, slot: int, src: int) -> int:
+        return self._mail(owner) + 8 * (slot * self.max_peers + src)
+
+    def _pulled_ptr(self, owner: int, slot: int, src: int) -> int:
+        return self._mail(owner) + 8 * ((self.slots + slot) * self.max_peers + src)
+
+    @property
+    def err_ptr(self) -> int:
+        return self._mail(self.rank) + self.MAILBOX_BYTES - 8
+
+    def my_slice(self):
+        """(offset, length) of this rank's slice of the logical byte range [0, nbytes)."""
+        lo = self.rank * self.chunk
+        return lo, max(0, min(self.nbytes, lo + self.chunk) - lo)
+
+    def gather(self, slot: int, upload_my_slice, stream: int = 0):
+        """`upload_my_slice(dst_ptr, offset, length)` must queue the host-to-device copy of bytes [offset, offset+length)
+        of the inputs to dst_ptr on `stream`.  Afterwards (in stream order) the slot's buffer holds all nbytes."""
+        self.uses[slot] += 1
+        seq = self.uses[slot]
+        lib, me, W = self.lib, self.rank, self.world
+        lib.peer_wait(self._pulled_ptr(me, slot, 0), W, seq - 1, self.err_ptr, stream)
+        lo, n = self.my_slice()
+        if n:
+            upload_my_slice(self.buffer_ptr(slot) + lo, lo, n)
+        lib.peer_signal([self._ready_ptr(r, slot, me) for r in range(W)], seq, stream)
+        lib.peer_wait(self._ready_ptr(me, slot, 0), W, seq, self.err_ptr, stream)
+        for d in range(1, W):                       # staggered: rank r starts with r+1, so no peer is hit by all at once
+            r = (me + d) % W
+            off = r * self.chunk
+            m = max(0, min(self.nbytes, off + self.chunk) - off)
+            if m:
+                lib.peer_copy(self.buffer_ptr(slot) + off, self.buffer_ptr(slot, r) + off, m, stream)
+        lib.peer_signal([self._pulled_ptr(r, slot, me) for r in range(W)], seq, stream)
 
     def close(self):
         for r, b in enumerate(self.bases):

@@ -19,7 +19,7 @@ import torch
 from . import _native
 
 __all__ = ["abbeImage", "calculateFFTAerial", "calculateAerial", "AbbeEngine", "PreparedImage", "source_shifts",
-           "epsilon_n"]
+           "epsilon_n", "tensor_from_ptr"]
 
 
 def _require_cuda(device) -> torch.device:
@@ -44,6 +44,19 @@ def source_shifts(lightsource: torch.Tensor, pixelNumber: int) -> torch.Tensor:
 
 def _as_c64(t: torch.Tensor, dev: torch.device) -> torch.Tensor:
     return t.to(device=dev, dtype=torch.complex64, non_blocking=True).contiguous()
+
+
+class _DevPtr:
+    """Minimal __cuda_array_interface__ carrier so that torch can view memory this package allocated itself
+    (peer-mapped buffers come from cudaMalloc + CUDA IPC, not from torch's caching allocator)."""
+
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def tensor_from_ptr(ptr: int, n: int, dev, dtype=torch.float32) -> torch.Tensor:
+    typestr = {torch.float32: "<f4", torch.int32: "<i4", torch.int64: "<i8", torch.uint8: "|u1"}[dtype]
+    return torch.as_tensor(_DevPtr(ptr, n, typestr), device=dev)
 
 
 def _check_square(name: str, t, pn: int | None = None) -> int:
@@ -279,7 +292,7 @@ class AbbeEngine:
     # -- pipelined form of abbe_fft: stage inputs one image ahead --------------------------------
     def prepare(self, maskFT, pupilF, lightsource, pixelSize, deltaK, wavelength, *, stream=None, slot: int = 0,
                 shard=None, generic: bool = False, plan: _native.Plan | None = None,
-                upload_group=None) -> "PreparedImage":
+                upload_group=None, upload_peers=None) -> "PreparedImage":
         """First half of abbe_fft: upload the (host or device) inputs and extract the source points on `stream`
         (default: a per-engine copy stream), without touching the compute stream.  Host tensors should be
         pinned.  `slot` (0/1) selects one of two device staging sets, so that image i+1 can be prepared while
@@ -288,7 +301,10 @@ class AbbeEngine:
         `upload_group` (a torch.distributed group, all ranks passing the same host inputs): every rank uploads only
         its 1/world slice of each tensor over PCIe and the slices are exchanged with one all-gather per tensor over
         NVLink, instead of every rank pulling the full tensors through the host's memory system at once.  Give it
-        a group of its own (dist.new_group) so that it does not queue behind the intensity reduce."""
+        a group of its own (dist.new_group) so that it does not queue behind the intensity reduce.
+        `upload_peers` (a distributed.PeerStaging sized for the three tensors, all ranks passing the same host inputs):
+        the same 1/world upload, but the slices are exchanged by copy-engine transfers between peer-mapped staging
+        buffers (no kernel, nothing competes with the compute kernels for SMs); takes precedence over upload_group."""
         dev = self.device
         st = stream if stream is not None else self._copy_stream()
         with torch.cuda.device(dev), torch.cuda.stream(st):
@@ -300,14 +316,20 @@ class AbbeEngine:
             _check_square("lightsource", lightsource, pn)
             if plan is not None and plan.pn != pn:
                 raise _native.LithoError(f"pinned plan is for pn={plan.pn}, inputs have pn={pn}")
-            bufs = self._staging.get((slot, pn, lightsource.dtype))
-            if bufs is None:
-                bufs = self._staging[(slot, pn, lightsource.dtype)] = (
-                    torch.empty((pn, pn), dtype=torch.complex64, device=dev),
-                    torch.empty((pn, pn), dtype=torch.complex64, device=dev),
-                    torch.empty((pn, pn), dtype=lightsource.dtype, device=dev))
-            mft_d, pf_d, ls_d = bufs
-            if upload_group is not None and shard is not None and shard[1] > 1:
+            use_peers = upload_peers is not None and shard is not None and shard[1] > 1
+            if use_peers:
+                bufs = self._peer_views(upload_peers, slot, pn, lightsource)
+            else:
+                bufs = self._staging.get((slot, pn, lightsource.dtype))
+                if bufs is None:
+                    bufs = self._staging[(slot, pn, lightsource.dtype)] = (
+                        torch.empty((pn, pn), dtype=torch.complex64, device=dev),
+                        torch.empty((pn, pn), dtype=torch.complex64, device=dev),
+                        torch.empty((pn, pn), dtype=lightsource.dtype, device=dev))
+            mft_d, pf_d, ls_d = bufs[-3:]
+            if use_peers:
+                self._peer_upload(upload_peers, slot, bufs[0], (maskFT, pupilF, lightsource), st)
+            elif upload_group is not None and shard is not None and shard[1] > 1:
                 self._sharded_upload(bufs, (maskFT, pupilF, lightsource), shard, upload_group, slot)
             else:
                 mft_d.copy_(maskFT, non_blocking=True)
@@ -355,6 +377,46 @@ class AbbeEngine:
             if not finalize:
                 return None
             return self.finalize(prep.plan, intensity, prep.eps) if postprocess else self.unpermute(prep.plan, intensity)
+
+    @staticmethod
+    def peer_staging_bytes(pn: int, lightsource_dtype=torch.int64) -> int:
+        """Bytes a distributed.PeerStaging must hold per slot for prepare(upload_peers=...): maskFT, pupil, lightsource."""
+        return 2 * pn * pn * 8 + pn * pn * torch.empty(0, dtype=lightsource_dtype).element_size()
+
+    def _peer_views(self, peers, slot, pn, lightsource):
+        """(uint8 view of the slot's buffer, maskFT, pupil, lightsource) as tensors over a PeerStaging buffer."""
+        key = ("peerviews", slot, pn, lightsource.dtype, peers.buffer_ptr(slot))
+        v = self._staging.get(key)
+        if v is None:
+            nb = pn * pn * 8
+            total = self.peer_staging_bytes(pn, lightsource.dtype)
+            if peers.nbytes != total:
+                raise _native.LithoError(f"PeerStaging holds {peers.nbytes} bytes per slot, these inputs need {total}")
+            u8 = tensor_from_ptr(peers.buffer_ptr(slot), total, self.device, torch.uint8)
+            mft_d = torch.view_as_complex(u8[:nb].view(torch.float32).view(pn, pn, 2))
+            pf_d = torch.view_as_complex(u8[nb:2 * nb].view(torch.float32).view(pn, pn, 2))
+            ls_d = u8[2 * nb:].view(lightsource.dtype).view(pn, pn)
+            v = self._staging[key] = (u8, mft_d, pf_d, ls_d)
+        return v
+
+    def _peer_upload(self, peers, slot, u8, host_tensors, st):
+        """H2D of this rank's byte slice of [maskFT | pupil | lightsource] + copy-engine gather of the other slices."""
+        segs, start = [], 0
+        for k, src in enumerate(host_tensors):
+            src = src.contiguous()
+            if k < 2 and src.dtype != torch.complex64:
+                src = src.to(torch.complex64)
+            flat = torch.view_as_real(src).view(-1).view(torch.uint8) if src.is_complex() else src.view(-1).view(torch.uint8)
+            segs.append((start, flat))
+            start += flat.numel()
+
+        def upload_my_slice(dst_ptr, off, n):
+            for s0, flat in segs:
+                a, b = max(off, s0), min(off + n, s0 + flat.numel())
+                if a < b:
+                    u8[a:b].copy_(flat[a - s0:b - s0], non_blocking=True)
+
+        peers.gather(slot, upload_my_slice, st.cuda_stream)
 
     def _sharded_upload(self, dev_bufs, host_tensors, shard, group, slot):
         """H2D of this rank's byte slice of each input + all-gather of the slices (current stream = copy stream)."""

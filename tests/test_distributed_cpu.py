@@ -142,3 +142,48 @@ def test_two_rank_peer_memory_sum_rotating_root(tmp_path):
     for i in range(5):
         img = np.load(str(tmp_path / f"img{i}.npy"))
         assert O.rel_l2(img, ref) < H.TOL
+
+
+def _staging_worker(rank, world, port, out_dir):
+    """distributed.PeerStaging between processes on the CPU emulation: every rank contributes its slice of a byte
+    range whose length is not a multiple of anything, 5 uses over 2 slots; every rank must end up with all bytes."""
+    import ctypes as C
+    from lithographysimulator_b200.distributed import PeerStaging
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lib = H.emu_lib()
+        nbytes = 100_003
+
+        def exchange(obj):
+            out = [None] * world
+            dist.all_gather_object(out, obj)
+            return out
+
+        st = PeerStaging(lib, nbytes, rank, world, exchange)
+        ok = True
+        for use in range(5):
+            slot = use % 2
+            data = ((np.arange(nbytes, dtype=np.int64) * (use + 3) + 7 * use) % 251).astype(np.uint8)   # same on all ranks
+
+            def upload(dst_ptr, off, n, data=data):
+                C.memmove(dst_ptr, data[off:off + n].ctypes.data, n)
+
+            st.gather(slot, upload)
+            got = np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(st.buffer_ptr(slot)))
+            ok = ok and bool((got == data).all())
+        err = (C.c_int * 2).from_address(st.err_ptr)
+        ok = ok and err[0] == 0
+        dist.barrier()
+        st.close()
+        open(os.path.join(out_dir, f"ok{rank}"), "w").write(str(ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_staging_gathers_all_slices(tmp_path):
+    H.emu_lib()
+    mp.spawn(_staging_worker, args=(3, _free_port(), str(tmp_path)), nprocs=3, join=True)
+    for r in range(3):
+        assert open(str(tmp_path / f"ok{r}")).read() == "True"

@@ -376,6 +376,22 @@ def _dist_worker(rank, world, port, out_path):
         img2 = eng.run(prep, reduce_fn=lambda t: dist.all_reduce(t))
         torch.cuda.synchronize(dev)
         assert torch.equal(img, img2), "sharded upload + prepare/run differs from abbe_image_sharded"
+        # the same staging with copy-engine peer copies instead of the NCCL all-gather (distributed.PeerStaging)
+        from lithographysimulator_b200.distributed import PeerStaging
+
+        def exchange(obj):
+            out = [None] * world
+            dist.all_gather_object(out, obj)
+            return out
+        stg = PeerStaging(eng.lib, AbbeEngine.peer_staging_bytes(cfg.pn, host[2].dtype), rank, world, exchange)
+        for use in range(3):        # slot 0, 1, 0: the third use re-fills a slot the peer has pulled from
+            prep = eng.prepare(host[0], host[1], host[2], cfg.pixel_size, m.deltaK, cfg.wavelength, slot=use % 2,
+                               shard=(rank, world), upload_peers=stg)
+            img3 = eng.run(prep, reduce_fn=lambda t: dist.all_reduce(t))
+            torch.cuda.synchronize(dev)
+            assert torch.equal(img, img3), f"peer-staged upload differs (use {use})"
+        dist.barrier()
+        stg.close()
         # pipelined throughput mode: 5 images, rotating root, partial planes summed over peer memory (CUDA IPC
         # + NVLink loads) and, for comparison, by ncclReduce; every image a root produced must equal `img`
         from lithographysimulator_b200.distributed import ShardedPipeline, shard_shifts
