@@ -16,6 +16,7 @@
 #include "../../include/litho_b200.h"
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -78,7 +79,7 @@ __global__ void peer_wait_kernel(const unsigned long long* flags, int n, unsigne
 }
 
 // out[i] = planes[0][i] + planes[1][i] + ... (rank order), 16-byte loads that bypass L1 (peer data)
-__global__ void __launch_bounds__(256) peer_sum_kernel(float* __restrict__ out, const __grid_constant__ PeerPtrs P,
+__global__ void __launch_bounds__(512) peer_sum_kernel(float* __restrict__ out, const __grid_constant__ PeerPtrs P,
                                                        unsigned long long elems, const unsigned long long* flags,
                                                        unsigned long long value, int* err) {
     if (flags) {   // (re-)acquire in this CTA: everything the producers published before their release is visible
@@ -312,12 +313,14 @@ int litho_peer_sum(float* out, const float* const* planes, int n, uint64_t elems
         P.p[r] = const_cast<float*>(planes[r]);
     }
     if (((uintptr_t)out & 15) != 0) return pfail(LITHO_ERR_ARG, "peer_sum: out must be 16-byte aligned");
-    int dev = 0, sms = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    unsigned long long want = (elems / 4 + 255) / 256;
-    const unsigned long long cap = (unsigned long long)sms * 4;   // grid-stride: a multiple of the SM count
+    // Few, long-lived CTAs: the sum usually runs next to persistent compute kernels that hold every register of every
+    // SM, so each of its CTAs has to wait for one of theirs to retire -- 64 CTAs x 512 threads with n x 16 bytes in
+    // flight per thread saturate the NVLink ingress and need 64 slot hand-overs instead of ~600 (LITHO_PEER_SUM_CTAS).
+    static const int cap_env = []() { const char* e = getenv("LITHO_PEER_SUM_CTAS"); return e ? atoi(e) : 64; }();
+    unsigned long long want = (elems / 4 + 511) / 512;
+    const unsigned long long cap = (unsigned long long)(cap_env > 0 ? cap_env : 64);
     const int grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));
-    peer_sum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(out, P, (unsigned long long)elems,
+    peer_sum_kernel<<<grid, 512, 0, (cudaStream_t)stream>>>(out, P, (unsigned long long)elems,
                                                             (const unsigned long long*)flags, (unsigned long long)value, err);
     PCHECK(cudaGetLastError());
 #endif
