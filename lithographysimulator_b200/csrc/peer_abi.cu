@@ -112,6 +112,35 @@ __global__ void __launch_bounds__(512) peer_sum_kernel(float* __restrict__ out, 
 
 }  // namespace
 
+// Stream memory operations (cuStreamWriteValue64 / cuStreamWaitValue64): the flag is written / polled by the
+// stream's front end, not by a kernel.  That matters here: the flags are signalled and awaited between persistent
+// compute kernels that hold every register of every SM, where even a one-warp kernel has to wait for a CTA of
+// theirs to retire (~0.2 ms per tiny kernel at cfg3).  LITHO_PEER_MEMOPS=0 selects the kernels.
+#include <cuda.h>
+typedef CUresult (*write_value64_fn)(CUstream, CUdeviceptr, cuuint64_t, unsigned int);
+typedef CUresult (*wait_value64_fn)(CUstream, CUdeviceptr, cuuint64_t, unsigned int);
+static write_value64_fn g_write64 = nullptr;
+static wait_value64_fn g_wait64 = nullptr;
+static bool memops_available() {
+    static const bool ok = []() -> bool {
+        const char* env = getenv("LITHO_PEER_MEMOPS");
+        if (env && atoi(env) == 0) return false;
+        void* p1 = nullptr;
+        void* p2 = nullptr;
+        cudaDriverEntryPointQueryResult q1, q2;
+        if (cudaGetDriverEntryPoint("cuStreamWriteValue64", &p1, cudaEnableDefault, &q1) != cudaSuccess ||
+            q1 != cudaDriverEntryPointSuccess || !p1)
+            return false;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue64", &p2, cudaEnableDefault, &q2) != cudaSuccess ||
+            q2 != cudaDriverEntryPointSuccess || !p2)
+            return false;
+        g_write64 = (write_value64_fn)p1;
+        g_wait64 = (wait_value64_fn)p2;
+        return true;
+    }();
+    return ok;
+}
+
 #define PCHECK(expr)                                                                                     \
     do {                                                                                                 \
         cudaError_t _e = (expr);                                                                         \
@@ -240,6 +269,13 @@ int litho_peer_signal(void* const* flags, int n, uint64_t value, void* stream) {
     (void)stream;
     for (int i = 0; i < n; ++i) __atomic_store_n((uint64_t*)flags[i], value, __ATOMIC_RELEASE);
 #else
+    if (memops_available()) {
+        bool all = true;
+        for (int i = 0; i < n && all; ++i)   // default flags: ordered after prior work of the stream, with a memory barrier
+            all = g_write64((CUstream)stream, (CUdeviceptr)(uintptr_t)flags[i], (cuuint64_t)value, 0) == CUDA_SUCCESS;
+        if (all) return LITHO_OK;
+        // (an address the driver refuses: fall through to the kernel, which rewrites every flag)
+    }
     PeerPtrs P;
     memset(&P, 0, sizeof(P));
     P.n = n;
@@ -267,6 +303,14 @@ int litho_peer_wait(const void* flags, int n, uint64_t value, int* err, void* st
         }
     }
 #else
+    if (memops_available() && value > 0) {
+        bool all = true;
+        for (int i = 0; i < n && all; ++i)
+            all = g_wait64((CUstream)stream, (CUdeviceptr)((uintptr_t)flags + 8u * (unsigned)i), (cuuint64_t)value,
+                           CU_STREAM_WAIT_VALUE_GEQ) == CUDA_SUCCESS;
+        if (all) return LITHO_OK;   // (no time-out in this form: a lost peer blocks the stream)
+    }
+    if (value == 0) return LITHO_OK;   // flags start at 0
     peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const unsigned long long*)flags, n, (unsigned long long)value, err);
     PCHECK(cudaGetLastError());
 #endif
