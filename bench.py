@@ -615,8 +615,17 @@ def run_ours(args):
                                  "source points: the intermediate T (16.8 MB per source point) makes one HBM round trip",
                     "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
         }
-        # rows + cols per batch, plus per image: rim sums and the 6 interpolation kernels (fast path) + resample
-        launches_per_step = 2 * ((n_mine + batch - 1) // batch) + (8 if plan.path == 2 else 1)
+        # our kernels launched by rank 0 inside the timed region (checked against profiles/r03u_launches.csv): per image
+        # rows + cols per batch and, on the fast path with a coarse grid, rim_kernel + rim_reduce_kernel; per image this
+        # rank post-processes (every N-th): coarse_unperm, 2 row passes, 3 column launches, assemble, finalize (7; 1 on
+        # the generic path / without a coarse grid) and, with N > 1 and the peer sum, peer_sum_kernel
+        coarse = plan.path == 2 and N // (2 * plan.M) > 1
+        Sr_, Sc_ = plan.bbox[1] - plan.bbox[0] + 1, plan.bbox[3] - plan.bbox[2] + 1
+        rim = 2 if (coarse and (Sr_ > plan.M or Sc_ > plan.M)) else 0
+        per_image = 2 * ((n_mine + batch - 1) // batch) + rim
+        per_root = (7 if coarse else 1) + (1 if pipe.reduce == "peer" else 0)
+        rooted = len([i for i in range(args.steps) if i % world == 0])
+        launches_total = per_image * args.steps + per_root * rooted
         cpu, library = None, None
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
@@ -664,7 +673,7 @@ def run_ours(args):
                                "; partial planes summed in rank order by the root with loads over NVLink from the peers' "
                                "CUDA-IPC-mapped planes (litho_peer_sum), sequence flags instead of a collective"
                                if pipe.reduce == "peer" else "; one ncclReduce of the intensity plane per image"))},
-                "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
+                "clocks": clocks, "gpu_launches": launches_total,
                 "e2e": {"value": 1.0 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": e2e_steps, "rel_l2_vs_resident_path": e2e_check,
                         "how": "pinned host tensors -> AbbeEngine.prepare() (H2D + source-point extraction on a copy "
