@@ -64,7 +64,15 @@ struct FastShape {
     static constexpr int CTW1_OFF = (CPRE_N + 1) & ~1;
     static constexpr int CTW2_OFF = CTW1_OFF + (R1 - 1) * NS1;          // (global memory only)
     static constexpr int CTAB_SMEM_PAD = (CTW2_OFF + 1) & ~1;
-    static constexpr int ROW_TAB_ELEMS = ROW_COMPACT ? CTAB_SMEM_PAD : NTAB_PAD;
+    // M = 1024 (one FFT per warp, two radix-32 passes): the residue-1 pre-twiddle w_2M^u, u = g + 32 e, is folded away.
+    // Its register part w_64^e is a compile-time constant per register of the first pass; its thread part w_2M^g
+    // reaches the second pass in register e' = g of every thread (the exchange is a transpose), where it merges with
+    // the inter-pass twiddle: w_2M^e' * w_M^(e' g') = w_2M^(e' (2 g' + 1)).  The row pass then needs no pre table at
+    // all, just a second copy of the inter-pass table: 32 fewer shared-memory loads per residue-1 FFT.
+    static constexpr bool ROW_FOLD = (TG == 32 && Sh::NP == 2 && R1 == 32);
+    static constexpr int FOLD_ODD_OFF = (R1 - 1) * NS1;            // fold table: [tw1][tw1_odd]
+    static constexpr int FOLD_TAB_ELEMS = 2 * (R1 - 1) * NS1;
+    static constexpr int ROW_TAB_ELEMS = ROW_COMPACT ? CTAB_SMEM_PAD : (ROW_FOLD ? FOLD_TAB_ELEMS : NTAB_PAD);
     static constexpr size_t ROW_SMEM = (size_t)(ROW_TAB_ELEMS + ROW_GROUPS * Sh::SMEM_ELEMS) * sizeof(cplx);
     // cols kernel: CB adjacent columns per CTA, column fastest in the thread index (256 threads per CTA
     // where possible; CB >= 4 keeps every global request at full 32-byte sectors)
@@ -105,14 +113,32 @@ struct SmemTw {
 };
 
 // Row-pass twiddles: full shared-memory tables, or (FastShape::ROW_COMPACT) compact shared-memory tables + tw2 from global
+// w_64^e = exp(2 pi i e / 64), e = 0..31: the register part of the residue-1 pre-twiddle (FastShape::ROW_FOLD)
+LITHO_HD cplx w64(int e) {   // (e is a compile-time constant after unrolling: the tables fold to immediates)
+    const float W64_RE[32] = {1.f, 0.995184727f, 0.98078528f, 0.956940336f, 0.923879533f, 0.881921264f, 0.831469612f,
+                              0.773010453f, 0.707106781f, 0.634393284f, 0.555570233f, 0.471396737f, 0.382683432f,
+                              0.290284677f, 0.195090322f, 0.0980171403f, 0.f, -0.0980171403f, -0.195090322f,
+                              -0.290284677f, -0.382683432f, -0.471396737f, -0.555570233f, -0.634393284f, -0.707106781f,
+                              -0.773010453f, -0.831469612f, -0.881921264f, -0.923879533f, -0.956940336f, -0.98078528f,
+                              -0.995184727f};
+    const float W64_IM[32] = {0.f, 0.0980171403f, 0.195090322f, 0.290284677f, 0.382683432f, 0.471396737f, 0.555570233f,
+                              0.634393284f, 0.707106781f, 0.773010453f, 0.831469612f, 0.881921264f, 0.923879533f,
+                              0.956940336f, 0.98078528f, 0.995184727f, 1.f, 0.995184727f, 0.98078528f, 0.956940336f,
+                              0.923879533f, 0.881921264f, 0.831469612f, 0.773010453f, 0.707106781f, 0.634393284f,
+                              0.555570233f, 0.471396737f, 0.382683432f, 0.290284677f, 0.195090322f, 0.0980171403f};
+    return mk(W64_RE[e], W64_IM[e]);
+}
+
 template <int M, int PPT>
 struct RowTw {
-    const cplx* tab;
+    const cplx* tab;    // ROW_FOLD: already offset to the table of this item's residue
     const cplx* gtab;
     template <int PASS>
     LITHO_HD cplx get(int t, int k) const {
         using F = FastShape<M, PPT>;
-        if constexpr (!F::ROW_COMPACT) {
+        if constexpr (F::ROW_FOLD) {
+            return tab[(t - 1) * F::NS1 + k];
+        } else if constexpr (!F::ROW_COMPACT) {
             if constexpr (PASS == 1) return tab[F::TW1_OFF + (t - 1) * F::NS1 + k];
             else return tab[F::TW2_OFF + (t - 1) * F::NS2 + k];
         } else {
@@ -157,6 +183,7 @@ struct FastRowsParams {
     int s_begin, batch;
     const cplx* tables;
     const cplx* tables_c;   // compact tables (TmaShape layout), used by the row pass when FastShape::ROW_COMPACT
+    const cplx* tables_r;   // [tw1][tw1_odd], used by the row pass when FastShape::ROW_FOLD
     cplx* T;  // [n_focus][batch][2][Sr][M]
     int* status;  // plan-owned device words: [0] set to 1 when a shift had to be clamped (contract violated)
     // focus batching (BASELINE cfg5): n_focus pupil planes (pupil + f*pupil_stride) share the mask
@@ -264,8 +291,13 @@ LITHO_HD void fast_row_load(cplx (&v)[PPT], const FastRowsParams& P, int s, int 
         }
     }
     if (r) {
+        if constexpr (F::ROW_FOLD) {
 #pragma unroll
-        for (int e = 0; e < PPT; ++e) v[e] = cmul(v[e], row_pre<M, PPT>(tab, g, e));
+            for (int e = 1; e < PPT; ++e) v[e] = cmul(v[e], w64(e));   // (the thread part sits in the pass-1 table)
+        } else {
+#pragma unroll
+            for (int e = 0; e < PPT; ++e) v[e] = cmul(v[e], row_pre<M, PPT>(tab, g, e));
+        }
     }
 }
 
@@ -323,7 +355,10 @@ LITHO_HD void fast_rows_body(const FastRowsParams& P, const Ctx& ctx, cplx* smem
     using Sh = typename F::Sh;
     constexpr int TG = F::TG;
     cplx* tab = smem;
-    if constexpr (F::ROW_COMPACT) {
+    if constexpr (F::ROW_FOLD) {
+        for (int i = ctx.tid(); i < F::FOLD_TAB_ELEMS; i += ctx.bdim()) tab[i] = P.tables_r[i];
+        ctx.sync();
+    } else if constexpr (F::ROW_COMPACT) {
         for (int i = ctx.tid(); i < F::CTAB_SMEM_PAD; i += ctx.bdim()) tab[i] = P.tables_c[i];
         ctx.sync();
     } else {
@@ -336,12 +371,12 @@ LITHO_HD void fast_rows_body(const FastRowsParams& P, const Ctx& ctx, cplx* smem
     const int total = P.batch * P.Sr * 2 * nf;
     const int stride = ctx.gdx() * F::ROW_GROUPS;
     const int rounds = (total + stride - 1) / stride;
-    const RowTw<M, PPT> tw{tab, P.tables_c};
     const GroupSync<Ctx, F::ROW_SYNC> gs{ctx, 1 + grp, TG};
 
     for (int it = 0; it < rounds; ++it) {
         const int item = it * stride + ctx.bx() * F::ROW_GROUPS + grp;
         const bool active = item < total;
+        const RowTw<M, PPT> tw{tab + ((F::ROW_FOLD && (item & 1)) ? F::FOLD_ODD_OFF : 0), P.tables_c};
         // item = ((sl*Sr + line)*nf + f)*2 + r : residue fastest, then focus value, then window row, then source point
         const int r = item & 1;
         int li = item >> 1;

@@ -387,6 +387,7 @@ struct litho_plan {
     int tma_cols;    // > 0: columns per tile of the TMA-staged column kernel (0: plain global loads)
     int tma_box_rows;  // rows per TMA box (TmaShape::BOX_ROWS)
     cplx* tables_c;  // device: compact twiddle tables of the TMA-staged column kernel (owned by the plan)
+    cplx* tables_r;  // device: [tw1][tw1_odd] of the folded row pass (Mf = 1024; owned by the plan)
     // T ring bookkeeping across accumulate calls (LITHO_PHASE_INPUTS_READY): which ring the ev_cols events of
     // the last call refer to
     mutable const void* last_ws;
@@ -659,7 +660,7 @@ int litho_plan_create_lines(int pn, int N, const int* bbox, int lines, int flags
     }
     size_t per = (size_t)p->zp.R * p->Sr * p->zp.Wr * sizeof(cplx);
     // ---- fast path eligibility: even window fit S <= Mf+1, coarse grid Nc = 2*Mf no finer than N ----
-    p->path = 1; p->tables = nullptr; p->tables_c = nullptr; p->tma_box_rows = 0; p->Mf = p->Nc = p->q = 0; p->er = p->ec = -1;
+    p->path = 1; p->tables = nullptr; p->tables_c = nullptr; p->tables_r = nullptr; p->tma_box_rows = 0; p->Mf = p->Nc = p->q = 0; p->er = p->ec = -1;
     p->tma_cols = 0;
     p->status = nullptr; p->rim_scratch = nullptr; p->rim_stride = 0;
     p->last_ws = nullptr; p->last_batch = 0;
@@ -754,8 +755,29 @@ int litho_plan_create_lines(int pn, int N, const int* bbox, int lines, int flags
             if (rc != 0) {
                 be_free(p->tables);
                 if (p->tables_c) be_free(p->tables_c);
+    if (p->tables_r) be_free(p->tables_r);
                 delete p;
                 return fail(LITHO_ERR_CUDA, std::string("plan_create: compact tables: ") + be_errstr(rc));
+            }
+        }
+        if (Mf == 1024 && p->ppt == 32) {
+            // folded row pass (FastShape::ROW_FOLD): tw1[t][k] = w_M^(t k) and tw1_odd[t][k] = w_2M^(t (2k+1)), t = 1..31
+            std::vector<cplx> tr;
+            for (int odd = 0; odd < 2; ++odd)
+                for (int t = 1; t < 32; ++t)
+                    for (int k = 0; k < 32; ++k) {
+                        const double a = 2.0 * M_PI * (double)(t * (2 * k + odd)) / (2.0 * Mf);
+                        tr.push_back(mk((float)cos(a), (float)sin(a)));
+                    }
+            rc = be_malloc((void**)&p->tables_r, tr.size() * sizeof(cplx));
+            if (rc == 0) rc = be_h2d(p->tables_r, tr.data(), tr.size() * sizeof(cplx), 0);
+#if !defined(LITHO_EMU)
+            if (rc == 0) rc = (int)cudaStreamSynchronize(0);
+#endif
+            if (rc != 0) {
+                const std::string msg = std::string("plan_create: folded row tables: ") + be_errstr(rc);
+                litho_plan_destroy(p);
+                return fail(LITHO_ERR_CUDA, msg);
             }
         }
         p->er = p->Sr > Mf ? p->Sr - 1 - Mf : -1;
@@ -1041,7 +1063,7 @@ static int accumulate_impl(const litho_plan_t* p, const void* maskFT, const void
         memset(&fr, 0, sizeof(fr));
         fr.pupil = (const cplx*)pupil; fr.mask = (const cplx*)maskFT; fr.pn = p->pn;
         fr.pr0 = p->bbox[0]; fr.pc0 = p->bbox[2]; fr.Sr = p->Sr; fr.Sc = p->Sc;
-        fr.shifts = (const int2_*)shifts; fr.tables = p->tables; fr.tables_c = p->tables_c; fr.T = (cplx*)workspace;
+        fr.shifts = (const int2_*)shifts; fr.tables = p->tables; fr.tables_c = p->tables_c; fr.tables_r = p->tables_r; fr.T = (cplx*)workspace;
         fr.status = p->status;
         fr.n_focus = nf; fr.pupil_stride = pupil_stride;
         FastColsParams fc;

@@ -413,3 +413,23 @@ def test_emu_subfft_4096_multi_tile_tma_column_pass():
     for d0, d1 in shifts:
         ref += np.abs(O.calculate_fft_aerial(np.roll(pup, (int(d0), int(d1)), (0, 1)), mft, pn, 8192)) ** 2
     assert O.rel_l2(img, ref) < H.TOL
+
+
+def test_emu_subfft_1024_folded_row_pass():
+    """Sub-FFT 1024 (the cfg3 kernel shape) on a synthetic 1060-px grid with a dense 1027-px window (S = M + 3), N = 4096:
+    the row pass folds the residue-1 pre-twiddle into per-register constants and a second inter-pass table
+    (FastShape::ROW_FOLD).  Two source points in one batch, against the oracle."""
+    pn, win = 1060, 1027
+    ps = pn * 193.0 / (4 * 4096)
+    rng = np.random.default_rng(11)
+    lo = pn // 2 - win // 2
+    pup = np.zeros((pn, pn), np.complex64)
+    pup[lo:lo + win, lo:lo + win] = rng.standard_normal((win, win)) + 1j * rng.standard_normal((win, win))
+    mft = (rng.standard_normal((pn, pn)) + 1j * rng.standard_normal((pn, pn))).astype(np.complex64)
+    shifts = np.array([[3, -5], [-7, 11]], np.int32)
+    img, info = H.emu_abbe_fft(mft, pup, None, ps, 193.0, shifts=shifts, postprocess=False, batch=2)
+    assert info["path"] == 2 and info["M"] == 1024 and info["N"] == 4096, info
+    ref = np.zeros((pn, pn))
+    for d0, d1 in shifts:
+        ref += np.abs(O.calculate_fft_aerial(np.roll(pup, (int(d0), int(d1)), (0, 1)), mft, pn, 4096)) ** 2
+    assert O.rel_l2(img, ref) < H.TOL
