@@ -5,7 +5,8 @@
 #   scripts/sanitize.sh order   CPU: the emulation suite with the threads of a CTA run in reverse and in pseudo-random order
 #                               between barriers (LITHO_EMU_ORDER): a missing barrier makes the result order-dependent
 #   scripts/sanitize.sh gpu     B200: compute-sanitizer memcheck / racecheck / synccheck on the small GPU parity cases
-#                               (shared-memory exchange, TMA tile buffer + mbarrier, named barriers)
+#                               (shared-memory exchange, TMA tile buffer + mbarrier, named barriers, the tcgen05
+#                               direct-solver kernel, the two-stage rim sums)
 set -e
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
 CSRC=$ROOT/lithographysimulator_b200/csrc
@@ -32,7 +33,8 @@ order)
 gpu)
     for tool in memcheck racecheck synccheck; do
         compute-sanitizer --tool $tool --error-exitcode 9 \
-            python -m pytest $ROOT/tests/test_gpu_parity.py -m gpu -x -q -k "golden and (demo64 or np2_96 or wrap_128)" \
+            python -m pytest $ROOT/tests/test_gpu_parity.py -m gpu -x -q \
+            -k "(golden and (demo64 or np2_96 or wrap_128 or direct_64)) or (tensor_core_path and (64 or 128)) or input_validation" \
             || { echo "compute-sanitizer $tool reported errors"; exit 9; }
     done
     ;;
