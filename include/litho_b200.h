@@ -214,7 +214,10 @@ int litho_pupil_build(const float* aberrations_host, int n_ab, int pn, void* pup
  *   litho_peer_open    map another process's buffer here; litho_peer_close unmaps; litho_peer_free frees an owned one
  *   litho_peer_signal  after the work queued on `stream`: *flags[i] = value for i < n (flags may be remote)
  *   litho_peer_wait    block `stream` until flags[i] >= value for all i < n (flags: n consecutive uint64 in LOCAL
- *                      memory); after ~20 s it gives up and sets *err (device int, may be NULL) to 1
+ *                      memory).  Both use stream memory operations (cuStreamWriteValue64 / cuStreamWaitValue64: no
+ *                      kernel, so nothing has to find a free SM between persistent compute kernels) and fall back to
+ *                      one-warp kernels (LITHO_PEER_MEMOPS=0); the kernel form of the wait gives up after ~20 s and
+ *                      sets *err (device int, may be NULL) to 1, the memory-operation form blocks until signalled
  *   litho_peer_sum     out[e] = planes[0][e] + ... + planes[n-1][e], e < elems (16-byte aligned pointers; planes may
  *                      be remote).  flags/value (optional): every CTA re-acquires flags[r] >= value before loading. */
 #define LITHO_MAX_PEERS 16

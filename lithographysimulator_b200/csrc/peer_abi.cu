@@ -7,9 +7,10 @@
 // post-processing reads.  No collective kernel has to be co-scheduled on every GPU: the other ranks only publish
 // a sequence number when their accumulation is done and go on with the next image.  Ordering between processes is
 // carried by 64-bit sequence flags in the same peer-mapped buffers:
-//     producer:  (accumulation kernels) -> peer_signal_kernel: st.release.sys flag = seq
-//     consumer:  peer_wait_kernel: ld.acquire.sys flag >= seq -> peer_sum_kernel (each CTA re-acquires, then loads)
-// A wait gives up after ~20 s and raises an error word instead of hanging the GPU.
+//     producer:  (accumulation kernels) -> flag = seq     (cuStreamWriteValue64, or peer_signal_kernel: st.release.sys)
+//     consumer:  wait flag >= seq                         (cuStreamWaitValue64, or peer_wait_kernel: ld.acquire.sys)
+//                -> peer_sum_kernel (each CTA re-acquires the flags, then loads)
+// The kernel form of a wait gives up after ~20 s and raises an error word instead of hanging the GPU.
 //
 // With -DLITHO_EMU the same entry points work between PROCESSES of one host through POSIX shared memory, so that
 // the protocol is covered by the world-size-2 gloo tests (tests only).
