@@ -78,6 +78,16 @@ int litho_pupil_support_lines(const void* pupil, int pn, int lines, int* support
  * A fast plan (path 2) may only be used when these lie inside plan_info.shift_range. */
 int litho_shift_bounds(const int32_t* shifts, int n_src, int* bounds_host, void* stream);
 
+/* Source points of a light-source plane in ONE launch                  imageformation.py:59-60
+ *   shifts[k] = (row, col) - pn//2 of the non-zero elements of `lightsource` (pn x pn elements of elem_size 1/2/4/8
+ *   bytes; is_float: -0.0 counts as zero, as in torch.argwhere), in row-major order -- the reference's loop order.
+ * rank/world select the interleaved shard (point number o belongs to rank o % world, stored at index o / world;
+ * 0/1 for all points); at most `capacity` points are stored.  meta_host receives {n_all, n_mine, min d0, max d0,
+ * min d1, max d1} (bounds over ALL points, the argument of a fast plan's no-wrap check).  Synchronises `stream`.
+ * Replaces the ~10 small kernels of the torch op sequence when images are staged back to back. */
+int litho_source_points(const void* lightsource, int elem_size, int is_float, int pn, int rank, int world,
+                        int32_t* shifts, int capacity, int* meta_host, void* stream);
+
 /* Plan for abbeImage(fft=True) on a pn x pn grid with FFT-approximation length N.
  * litho_plan_create takes the 4-int bbox; litho_plan_create_ex the 12-int support of
  * litho_pupil_support (cheaper rim sums).  flags: 0 or LITHO_PLAN_GENERIC.

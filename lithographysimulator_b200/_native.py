@@ -40,6 +40,7 @@ SYMBOLS = [
     ("litho_pupil_support", C.c_int, [_P, C.c_int, C.POINTER(C.c_int), _P]),
     ("litho_pupil_support_lines", C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_int), _P]),
     ("litho_shift_bounds", C.c_int, [_P, C.c_int, C.POINTER(C.c_int), _P]),
+    ("litho_source_points", C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.POINTER(C.c_int), _P]),
     ("litho_plan_create", C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(_P)]),
     ("litho_plan_create_ex", C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(_P)]),
     ("litho_plan_create_lines", C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(_P)]),
@@ -163,6 +164,14 @@ class NativeLib:
         b = (C.c_int * 4)()
         self.check(self.litho_shift_bounds(shifts_ptr, n_src, b, stream), "litho_shift_bounds")
         return tuple(b)
+
+    def source_points(self, ls_ptr: int, elem_size: int, is_float: bool, pn: int, rank: int, world: int, shifts_ptr,
+                      capacity: int, stream: int = 0):
+        """(n_all, n_mine, (d0 min, d0 max, d1 min, d1 max)) -- see litho_source_points."""
+        meta = (C.c_int * 6)()
+        self.check(self.litho_source_points(ls_ptr, elem_size, 1 if is_float else 0, pn, rank, world, shifts_ptr, capacity,
+                                            meta, stream), "litho_source_points")
+        return int(meta[0]), int(meta[1]), (int(meta[2]), int(meta[3]), int(meta[4]), int(meta[5]))
 
     def plan_create(self, pn: int, N: int, support, flags: int = 0) -> "Plan":
         """`support` is the 4-int bbox or the (4 + 8*lines)-int result of pupil_support()."""

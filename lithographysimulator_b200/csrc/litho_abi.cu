@@ -184,6 +184,84 @@ __global__ void __launch_bounds__(256) fma_probe_kernel(float* out, int iters) {
     for (int i = 0; i < 16; ++i) s += a[i];
     if (s == 12345.678f) out[0] = s;  // never true: keeps the loop alive without memory traffic
 }
+// Source-point extraction in ONE launch (imageformation.py:59: argwhere(lightsource) - pn//2, row-major order), for
+// callers that stage one image after another next to persistent compute kernels, where every extra tiny kernel of
+// the torch op sequence (nonzero, sub, cast, slice, bounds) waits ~0.1 ms for a free SM slot.  One 1024-thread CTA
+// streams the plane in row-major order, 16 coalesced loads per thread in flight; a sub-chunk of 1024 elements is
+// compacted with warp ballots + a 32-entry shared prefix, sub-chunks without a source point (almost all) cost one
+// barrier.  Point number o (in reference order) goes to this rank iff o % world == rank, at index o / world.
+struct SourcePointsParams {
+    const unsigned char* ls;
+    int elem_size, is_float, pn, rank, world, capacity;
+    int2_* out;
+    int* meta;   // {n_all, n_mine, min d0, max d0, min d1, max d1} (bounds over ALL points)
+};
+__device__ __forceinline__ bool sp_nonzero(const unsigned char* p, size_t i, int es, int is_float) {
+    switch (es) {
+        case 8: { const unsigned long long v = reinterpret_cast<const unsigned long long*>(p)[i];
+                  return is_float ? (v << 1) != 0ull : v != 0ull; }
+        case 4: { const unsigned v = reinterpret_cast<const unsigned*>(p)[i]; return is_float ? (v << 1) != 0u : v != 0u; }
+        case 2: { const unsigned short v = reinterpret_cast<const unsigned short*>(p)[i];
+                  return is_float ? (unsigned short)(v << 1) != 0 : v != 0; }
+        default: return p[i] != 0;
+    }
+}
+__global__ void __launch_bounds__(1024) source_points_kernel(const __grid_constant__ SourcePointsParams P) {
+    __shared__ int warp_cnt[32];
+    __shared__ int s_running;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const size_t total = (size_t)P.pn * P.pn;
+    const int half = P.pn / 2;
+    int lo0 = INT32_MAX, hi0 = INT32_MIN, lo1 = INT32_MAX, hi1 = INT32_MIN;
+    if (t == 0) s_running = 0;
+    __syncthreads();
+    for (size_t base = 0; base < total; base += (size_t)16 * 1024) {
+        unsigned flags = 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const size_t i = base + (size_t)k * 1024 + t;
+            if (i < total && sp_nonzero(P.ls, i, P.elem_size, P.is_float)) flags |= 1u << k;
+        }
+        if (!__syncthreads_or((int)flags)) continue;
+        for (int k = 0; k < 16; ++k) {
+            const bool f = (flags >> k) & 1u;
+            if (!__syncthreads_or((int)f)) continue;
+            const unsigned b = __ballot_sync(0xffffffffu, f);
+            if (lane == 0) warp_cnt[w] = __popc(b);
+            __syncthreads();
+            int before = 0, all = 0;
+            for (int j = 0; j < 32; ++j) {
+                const int c = warp_cnt[j];
+                before += j < w ? c : 0;
+                all += c;
+            }
+            const int running = s_running;
+            if (f) {
+                const int o = running + before + __popc(b & ((1u << lane) - 1u));
+                const size_t i = base + (size_t)k * 1024 + t;
+                const int d0 = (int)(i / P.pn) - half, d1 = (int)(i % P.pn) - half;
+                lo0 = min(lo0, d0); hi0 = max(hi0, d0); lo1 = min(lo1, d1); hi1 = max(hi1, d1);
+                if (o % P.world == P.rank) {
+                    const int idx = o / P.world;
+                    if (idx < P.capacity) { P.out[idx].x = d0; P.out[idx].y = d1; }
+                }
+            }
+            __syncthreads();
+            if (t == 0) s_running = running + all;
+            __syncthreads();
+        }
+    }
+    if (hi0 >= lo0) {
+        atomicMin(P.meta + 2, lo0); atomicMax(P.meta + 3, hi0);
+        atomicMin(P.meta + 4, lo1); atomicMax(P.meta + 5, hi1);
+    }
+    __syncthreads();
+    if (t == 0) {
+        const int n = s_running;
+        P.meta[0] = n;
+        P.meta[1] = n > P.rank ? (n - P.rank + P.world - 1) / P.world : 0;
+    }
+}
 __global__ void bbox_kernel(const __grid_constant__ BBoxParams P) { bbox_body(P, DevCtx{}); }
 __global__ void ext_kernel(const __grid_constant__ ExtParams P) { ext_body(P, DevCtx{}); }
 __global__ void shift_bounds_kernel(const __grid_constant__ ShiftBoundsParams P) { shift_bounds_body(P, DevCtx{}); }
@@ -610,6 +688,54 @@ int litho_shift_bounds(const int32_t* shifts, int n_src, int* bounds_host, void*
     }
     if (rc == 0) rc = be_d2h_sync(bounds_host, d, 4 * sizeof(int), st);
     if (rc != 0) return fail(LITHO_ERR_CUDA, std::string("shift_bounds: ") + be_errstr(rc));
+    return LITHO_OK;
+}
+
+int litho_source_points(const void* lightsource, int elem_size, int is_float, int pn, int rank, int world,
+                        int32_t* shifts, int capacity, int* meta_host, void* stream) {
+    if (!lightsource || !meta_host || pn < 1 || world < 1 || rank < 0 || rank >= world || capacity < 0 ||
+        (capacity > 0 && !shifts) || (elem_size != 1 && elem_size != 2 && elem_size != 4 && elem_size != 8))
+        return fail(LITHO_ERR_ARG, "source_points: bad argument");
+    litho_stream_t st = (litho_stream_t)stream;
+    int init[6] = {0, 0, INT32_MAX, INT32_MIN, INT32_MAX, INT32_MIN};
+#if defined(LITHO_EMU)
+    (void)st;
+    const unsigned char* p = (const unsigned char*)lightsource;
+    int n = 0, mine = 0;
+    for (size_t i = 0; i < (size_t)pn * pn; ++i) {
+        bool nz = false;
+        if (is_float && elem_size == 8) nz = ((const double*)p)[i] != 0.0;
+        else if (is_float && elem_size == 4) nz = ((const float*)p)[i] != 0.0f;
+        else if (is_float && elem_size == 2) nz = (unsigned short)(((const unsigned short*)p)[i] << 1) != 0;
+        else for (int b = 0; b < elem_size; ++b) nz = nz || p[i * elem_size + b] != 0;
+        if (!nz) continue;
+        const int d0 = (int)(i / pn) - pn / 2, d1 = (int)(i % pn) - pn / 2;
+        if (d0 < init[2]) init[2] = d0;
+        if (d0 > init[3]) init[3] = d0;
+        if (d1 < init[4]) init[4] = d1;
+        if (d1 > init[5]) init[5] = d1;
+        if (n % world == rank) {
+            if (mine < capacity) { shifts[2 * mine] = d0; shifts[2 * mine + 1] = d1; }
+            ++mine;
+        }
+        ++n;
+    }
+    init[0] = n; init[1] = mine;
+    memcpy(meta_host, init, sizeof(init));
+#else
+    std::lock_guard<std::mutex> scratch_lock(g_scratch_mutex);
+    int* dmeta = nullptr;
+    BE_CHECK(get_scratch(&dmeta));
+    BE_CHECK(be_h2d(dmeta, init, sizeof(init), st));
+    SourcePointsParams P;
+    memset(&P, 0, sizeof(P));
+    P.ls = (const unsigned char*)lightsource; P.elem_size = elem_size; P.is_float = is_float; P.pn = pn;
+    P.rank = rank; P.world = world; P.capacity = capacity; P.out = (int2_*)shifts; P.meta = dmeta;
+    source_points_kernel<<<1, 1024, 0, st>>>(P);
+    BE_CHECK((int)cudaGetLastError());
+    BE_CHECK(be_d2h_sync(meta_host, dmeta, sizeof(init), st));
+#endif
+    if (meta_host[0] == 0) meta_host[2] = meta_host[3] = meta_host[4] = meta_host[5] = 0;
     return LITHO_OK;
 }
 

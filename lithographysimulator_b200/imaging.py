@@ -84,6 +84,7 @@ class AbbeEngine:
 
     _engines: dict = {}
     _lock = threading.Lock()
+    MAX_STAGED_POINTS = 1 << 20     # source points per rank the staging buffers of prepare() hold (8 MB per slot)
 
     def __init__(self, device: torch.device):
         self.device = device
@@ -336,25 +337,33 @@ class AbbeEngine:
                 pf_d.copy_(pupilF, non_blocking=True)
                 ls_d.copy_(lightsource, non_blocking=True)
             eps, N = epsilon_n(deltaK, pixelSize, wavelength)
-            shifts_all = source_shifts(ls_d, pn)       # host sync on the copy stream only
-            if plan is None:
-                support = self.lib.pupil_support(pf_d.data_ptr(), pn, st.cuda_stream)
-                if generic:
-                    plan = self.plan(pn, N, support, generic=True)
-                else:
-                    plan = self.plan(pn, N, support)
-                    if plan.path == 2:
-                        n = int(shifts_all.shape[0])
-                        bounds = self.lib.shift_bounds(shifts_all.data_ptr() if n else None, n, st.cuda_stream)
-                        if not plan.shifts_fit(bounds):
-                            plan = self.plan(pn, N, support, generic=True)
-            elif plan.path == 2:     # pinned fast plan: the no-wrap contract is checked here (copy stream only)
+            # source points of this rank's shard + the shift bounds of all points in ONE launch (litho_source_points;
+            # host sync on the copy stream only).  The torch op sequence costs ~10 small kernels, each of which waits
+            # for a free SM slot next to the persistent compute kernels of the image being computed.
+            rank_, world_ = shard if shard is not None else (0, 1)
+            shifts = bounds = None
+            if not ls_d.is_complex():
+                sbuf = self._staging.get(("shifts", slot))
+                if sbuf is None:
+                    sbuf = self._staging[("shifts", slot)] = torch.empty((self.MAX_STAGED_POINTS, 2), dtype=torch.int32, device=dev)
+                n_all, n_mine, bounds = self.lib.source_points(ls_d.data_ptr(), ls_d.element_size(), ls_d.is_floating_point(),
+                                                               pn, rank_, world_, sbuf.data_ptr(), self.MAX_STAGED_POINTS,
+                                                               st.cuda_stream)
+                if n_mine <= self.MAX_STAGED_POINTS:
+                    shifts = sbuf[:n_mine]
+            if shifts is None:      # complex-valued source plane or more points than the staging buffer holds
+                shifts_all = source_shifts(ls_d, pn)
                 n = int(shifts_all.shape[0])
                 bounds = self.lib.shift_bounds(shifts_all.data_ptr() if n else None, n, st.cuda_stream)
-                if not plan.shifts_fit(bounds):
-                    raise _native.LithoError(f"pinned fast plan: source shifts {bounds} leave the plan's no-wrap range "
-                                             f"{plan.shift_range}")
-            shifts = shifts_all if shard is None else shifts_all[shard[0]::shard[1]].contiguous()
+                shifts = shifts_all if shard is None else shifts_all[shard[0]::shard[1]].contiguous()
+            if plan is None:
+                support = self.lib.pupil_support(pf_d.data_ptr(), pn, st.cuda_stream)
+                plan = self.plan(pn, N, support, generic=generic)
+                if plan.path == 2 and not plan.shifts_fit(bounds):
+                    plan = self.plan(pn, N, support, generic=True)
+            elif plan.path == 2 and not plan.shifts_fit(bounds):     # pinned fast plan: the no-wrap contract
+                raise _native.LithoError(f"pinned fast plan: source shifts {bounds} leave the plan's no-wrap range "
+                                         f"{plan.shift_range}")
             ready = torch.cuda.Event()
             ready.record(st)
         return PreparedImage(slot, mft_d, pf_d, shifts, plan, eps, ready)

@@ -881,3 +881,36 @@ def test_direct_solver_tensor_core_path(L, dev, pn):
         err = float((outs[tc] - ref).norm() / ref.norm())
         assert err < 1e-5, (tc, err)
     assert float((outs["1"] - outs["0"]).norm() / outs["0"].norm()) < 1e-5
+
+
+def test_source_points_kernel_matches_argwhere(L, dev):
+    """litho_source_points (one launch: ordered compaction of the non-zero source pixels, interleaved shard, shift
+    bounds) against torch.argwhere for sparse, dense and empty planes, every element size, -0.0, and shards."""
+    from lithographysimulator_b200 import _native
+    lib = _native.device_lib()
+    g = torch.Generator().manual_seed(3)
+    cases = []
+    for pn, density in ((64, 0.3), (250, 0.001), (256, 1.0), (1024, 0.0005), (2048, 0.00025), (128, 0.0)):
+        base = (torch.rand((pn, pn), generator=g) < density)
+        for dt in (torch.int64, torch.int32, torch.int16, torch.uint8, torch.bool, torch.float32, torch.float16, torch.float64):
+            t = base.to(dt)
+            if dt.is_floating_point:
+                t = t * 2.5
+                t[0, 0] = -0.0           # negative zero is not a source point
+            cases.append((pn, t))
+    for pn, t in cases[:: 3] + cases[1:: 7]:
+        t_d = t.to(dev)
+        ref = (torch.argwhere(t_d) - pn // 2).to(torch.int32)
+        n = int(ref.shape[0])
+        for rank, world in ((0, 1), (1, 3), (7, 8)):
+            cap = max(1, n)
+            out = torch.full((cap, 2), -12345, dtype=torch.int32, device=dev)
+            n_all, n_mine, bounds = lib.source_points(t_d.data_ptr(), t_d.element_size(), t_d.is_floating_point(), pn, rank,
+                                                      world, out.data_ptr(), cap, torch.cuda.current_stream(dev).cuda_stream)
+            mine = ref[rank::world]
+            assert n_all == n and n_mine == int(mine.shape[0]), (pn, t.dtype, rank, world, n_all, n, n_mine)
+            assert torch.equal(out[:n_mine], mine), (pn, t.dtype, rank, world)
+            if n:
+                assert bounds == (int(ref[:, 0].min()), int(ref[:, 0].max()), int(ref[:, 1].min()), int(ref[:, 1].max()))
+            else:
+                assert bounds == (0, 0, 0, 0)
