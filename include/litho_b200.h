@@ -78,7 +78,7 @@ int litho_pupil_support_lines(const void* pupil, int pn, int lines, int* support
  * A fast plan (path 2) may only be used when these lie inside plan_info.shift_range. */
 int litho_shift_bounds(const int32_t* shifts, int n_src, int* bounds_host, void* stream);
 
-/* Source points of a light-source plane in ONE launch                  imageformation.py:59-60
+/* Source points of a light-source plane in two short launches         imageformation.py:59-60
  *   shifts[k] = (row, col) - pn//2 of the non-zero elements of `lightsource` (pn x pn elements of elem_size 1/2/4/8
  *   bytes; is_float: -0.0 counts as zero, as in torch.argwhere), in row-major order -- the reference's loop order.
  * rank/world select the interleaved shard (point number o belongs to rank o % world, stored at index o / world;

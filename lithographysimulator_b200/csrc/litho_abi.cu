@@ -184,17 +184,21 @@ __global__ void __launch_bounds__(256) fma_probe_kernel(float* out, int iters) {
     for (int i = 0; i < 16; ++i) s += a[i];
     if (s == 12345.678f) out[0] = s;  // never true: keeps the loop alive without memory traffic
 }
-// Source-point extraction in ONE launch (imageformation.py:59: argwhere(lightsource) - pn//2, row-major order), for
-// callers that stage one image after another next to persistent compute kernels, where every extra tiny kernel of
-// the torch op sequence (nonzero, sub, cast, slice, bounds) waits ~0.1 ms for a free SM slot.  One 1024-thread CTA
-// streams the plane in row-major order, 16 coalesced loads per thread in flight; a sub-chunk of 1024 elements is
-// compacted with warp ballots + a 32-entry shared prefix, sub-chunks without a source point (almost all) cost one
-// barrier.  Point number o (in reference order) goes to this rank iff o % world == rank, at index o / world.
+// Source-point extraction in two short launches (imageformation.py:59: argwhere(lightsource) - pn//2, row-major
+// order), for callers that stage one image after another next to persistent compute kernels, where every extra
+// small kernel of the torch op sequence (nonzero, sub, cast, slice, bounds: ~10 launches) waits ~0.1 ms for a free
+// SM slot.  The plane is cut into SP_CTAS contiguous chunks: pass 1 counts the source points of each chunk, pass 2
+// gives every CTA the sum of the counts before it and compacts its chunk in order (warp ballots + an 8-entry shared
+// prefix per 256-element sub-chunk; sub-chunks without a source point -- almost all -- cost one barrier).  Point
+// number o (in reference order) goes to this rank iff o % world == rank, at index o / world.
+#define SP_CTAS 296
 struct SourcePointsParams {
     const unsigned char* ls;
     int elem_size, is_float, pn, rank, world, capacity;
     int2_* out;
-    int* meta;   // {n_all, n_mine, min d0, max d0, min d1, max d1} (bounds over ALL points)
+    int* meta;     // {n_all, n_mine, min d0, max d0, min d1, max d1} (bounds over ALL points)
+    int* counts;   // [SP_CTAS]
+    size_t chunk;  // elements per CTA (a multiple of 256)
 };
 __device__ __forceinline__ bool sp_nonzero(const unsigned char* p, size_t i, int es, int is_float) {
     switch (es) {
@@ -206,60 +210,84 @@ __device__ __forceinline__ bool sp_nonzero(const unsigned char* p, size_t i, int
         default: return p[i] != 0;
     }
 }
-__global__ void __launch_bounds__(1024) source_points_kernel(const __grid_constant__ SourcePointsParams P) {
-    __shared__ int warp_cnt[32];
+__global__ void __launch_bounds__(256) source_count_kernel(const __grid_constant__ SourcePointsParams P) {
+    const size_t total = (size_t)P.pn * P.pn;
+    const size_t lo = (size_t)blockIdx.x * P.chunk, hi = lo + P.chunk < total ? lo + P.chunk : total;
+    int c = 0;
+    for (size_t i = lo + threadIdx.x; i < hi; i += 256) c += sp_nonzero(P.ls, i, P.elem_size, P.is_float) ? 1 : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    __shared__ int wc[8];
+    if ((threadIdx.x & 31) == 0) wc[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int j = 0; j < 8; ++j) s += wc[j];
+        P.counts[blockIdx.x] = s;
+    }
+}
+__global__ void __launch_bounds__(256) source_compact_kernel(const __grid_constant__ SourcePointsParams P) {
+    __shared__ int warp_cnt[8];
     __shared__ int s_running;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     const size_t total = (size_t)P.pn * P.pn;
+    const size_t lo = (size_t)blockIdx.x * P.chunk, hi = lo + P.chunk < total ? lo + P.chunk : total;
     const int half = P.pn / 2;
+    {   // points before this chunk, and (CTA 0) the grand total
+        int before = 0, all = 0;
+        for (int j = t; j < SP_CTAS; j += 256) {
+            const int c = P.counts[j];
+            all += c;
+            before += j < (int)blockIdx.x ? c : 0;
+        }
+        before = __reduce_add_sync(0xffffffffu, before);
+        all = __reduce_add_sync(0xffffffffu, all);
+        __shared__ int wb[8], wa[8];
+        if (lane == 0) { wb[w] = before; wa[w] = all; }
+        __syncthreads();
+        if (t == 0) {
+            int sb = 0, sa = 0;
+            for (int j = 0; j < 8; ++j) { sb += wb[j]; sa += wa[j]; }
+            s_running = sb;
+            if (blockIdx.x == 0) {
+                P.meta[0] = sa;
+                P.meta[1] = sa > P.rank ? (sa - P.rank + P.world - 1) / P.world : 0;
+            }
+        }
+        __syncthreads();
+    }
+    if (P.counts[blockIdx.x] == 0) return;
     int lo0 = INT32_MAX, hi0 = INT32_MIN, lo1 = INT32_MAX, hi1 = INT32_MIN;
-    if (t == 0) s_running = 0;
-    __syncthreads();
-    for (size_t base = 0; base < total; base += (size_t)16 * 1024) {
-        unsigned flags = 0;
+    for (size_t base = lo; base < hi; base += 256) {
+        const size_t i = base + t;
+        const bool f = i < hi && sp_nonzero(P.ls, i, P.elem_size, P.is_float);
+        if (!__syncthreads_or((int)f)) continue;
+        const unsigned b = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) warp_cnt[w] = __popc(b);
+        __syncthreads();
+        int before = 0, all = 0;
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const size_t i = base + (size_t)k * 1024 + t;
-            if (i < total && sp_nonzero(P.ls, i, P.elem_size, P.is_float)) flags |= 1u << k;
+        for (int j = 0; j < 8; ++j) {
+            const int c = warp_cnt[j];
+            before += j < w ? c : 0;
+            all += c;
         }
-        if (!__syncthreads_or((int)flags)) continue;
-        for (int k = 0; k < 16; ++k) {
-            const bool f = (flags >> k) & 1u;
-            if (!__syncthreads_or((int)f)) continue;
-            const unsigned b = __ballot_sync(0xffffffffu, f);
-            if (lane == 0) warp_cnt[w] = __popc(b);
-            __syncthreads();
-            int before = 0, all = 0;
-            for (int j = 0; j < 32; ++j) {
-                const int c = warp_cnt[j];
-                before += j < w ? c : 0;
-                all += c;
+        const int running = s_running;
+        if (f) {
+            const int o = running + before + __popc(b & ((1u << lane) - 1u));
+            const int d0 = (int)(i / P.pn) - half, d1 = (int)(i % P.pn) - half;
+            lo0 = min(lo0, d0); hi0 = max(hi0, d0); lo1 = min(lo1, d1); hi1 = max(hi1, d1);
+            if (o % P.world == P.rank) {
+                const int idx = o / P.world;
+                if (idx < P.capacity) { P.out[idx].x = d0; P.out[idx].y = d1; }
             }
-            const int running = s_running;
-            if (f) {
-                const int o = running + before + __popc(b & ((1u << lane) - 1u));
-                const size_t i = base + (size_t)k * 1024 + t;
-                const int d0 = (int)(i / P.pn) - half, d1 = (int)(i % P.pn) - half;
-                lo0 = min(lo0, d0); hi0 = max(hi0, d0); lo1 = min(lo1, d1); hi1 = max(hi1, d1);
-                if (o % P.world == P.rank) {
-                    const int idx = o / P.world;
-                    if (idx < P.capacity) { P.out[idx].x = d0; P.out[idx].y = d1; }
-                }
-            }
-            __syncthreads();
-            if (t == 0) s_running = running + all;
-            __syncthreads();
         }
+        __syncthreads();
+        if (t == 0) s_running = running + all;
+        __syncthreads();
     }
     if (hi0 >= lo0) {
         atomicMin(P.meta + 2, lo0); atomicMax(P.meta + 3, hi0);
         atomicMin(P.meta + 4, lo1); atomicMax(P.meta + 5, hi1);
-    }
-    __syncthreads();
-    if (t == 0) {
-        const int n = s_running;
-        P.meta[0] = n;
-        P.meta[1] = n > P.rank ? (n - P.rank + P.world - 1) / P.world : 0;
     }
 }
 __global__ void bbox_kernel(const __grid_constant__ BBoxParams P) { bbox_body(P, DevCtx{}); }
@@ -725,13 +753,18 @@ int litho_source_points(const void* lightsource, int elem_size, int is_float, in
 #else
     std::lock_guard<std::mutex> scratch_lock(g_scratch_mutex);
     int* dmeta = nullptr;
-    BE_CHECK(get_scratch(&dmeta));
+    BE_CHECK(get_scratch(&dmeta));      // scratch: meta (6 ints, padded to 16), then the per-chunk counts
     BE_CHECK(be_h2d(dmeta, init, sizeof(init), st));
     SourcePointsParams P;
     memset(&P, 0, sizeof(P));
     P.ls = (const unsigned char*)lightsource; P.elem_size = elem_size; P.is_float = is_float; P.pn = pn;
     P.rank = rank; P.world = world; P.capacity = capacity; P.out = (int2_*)shifts; P.meta = dmeta;
-    source_points_kernel<<<1, 1024, 0, st>>>(P);
+    P.counts = dmeta + 16;
+    const size_t total = (size_t)pn * pn;
+    P.chunk = ((total + SP_CTAS - 1) / SP_CTAS + 255) / 256 * 256;
+    source_count_kernel<<<SP_CTAS, 256, 0, st>>>(P);
+    BE_CHECK((int)cudaGetLastError());
+    source_compact_kernel<<<SP_CTAS, 256, 0, st>>>(P);
     BE_CHECK((int)cudaGetLastError());
     BE_CHECK(be_d2h_sync(meta_host, dmeta, sizeof(init), st));
 #endif

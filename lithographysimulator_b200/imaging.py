@@ -337,7 +337,7 @@ class AbbeEngine:
                 pf_d.copy_(pupilF, non_blocking=True)
                 ls_d.copy_(lightsource, non_blocking=True)
             eps, N = epsilon_n(deltaK, pixelSize, wavelength)
-            # source points of this rank's shard + the shift bounds of all points in ONE launch (litho_source_points;
+            # source points of this rank's shard + the shift bounds of all points in two short launches (litho_source_points;
             # host sync on the copy stream only).  The torch op sequence costs ~10 small kernels, each of which waits
             # for a free SM slot next to the persistent compute kernels of the image being computed.
             rank_, world_ = shard if shard is not None else (0, 1)

@@ -884,7 +884,7 @@ def test_direct_solver_tensor_core_path(L, dev, pn):
 
 
 def test_source_points_kernel_matches_argwhere(L, dev):
-    """litho_source_points (one launch: ordered compaction of the non-zero source pixels, interleaved shard, shift
+    """litho_source_points (count + compact launches: ordered compaction of the non-zero source pixels, interleaved shard, shift
     bounds) against torch.argwhere for sparse, dense and empty planes, every element size, -0.0, and shards."""
     from lithographysimulator_b200 import _native
     lib = _native.device_lib()
