@@ -80,7 +80,12 @@ class PreparedImage:
 
 
 class AbbeEngine:
-    """Per-device cache of plans and workspaces for the FFT-approximation path."""
+    """Per-device cache of plans and workspaces for the FFT-approximation path.
+
+    Threading: the caches are guarded by a lock, but a plan carries per-call state of its own (T-ring events, an
+    auxiliary stream; include/litho_b200.h) and every fast plan owns its T ring, so one engine drives ONE stream of
+    images at a time.  Callers that want two concurrent streams on a device use two plans (different pupils get
+    different plans anyway) and serialise calls that share a plan."""
 
     _engines: dict = {}
     _lock = threading.Lock()
@@ -94,6 +99,7 @@ class AbbeEngine:
         self._staging: dict = {}        # (slot, pn, source dtype) -> device copies of maskFT, pupil, lightsource
         self._staging_busy: dict = {}   # slot -> event of the last run() that read the set
         self._copy = None
+        self._cache_lock = threading.Lock()
 
     @classmethod
     def get(cls, device) -> "AbbeEngine":
@@ -117,9 +123,10 @@ class AbbeEngine:
 
     def plan(self, pn: int, N: int, support, generic: bool = False) -> _native.Plan:
         key = (pn, N, tuple(support), bool(generic))
-        p = self._plans.get(key)
-        if p is None:
-            p = self._plans[key] = self.lib.plan_create(pn, N, support, _native.PLAN_GENERIC if generic else 0)
+        with self._cache_lock:
+            p = self._plans.get(key)
+            if p is None:
+                p = self._plans[key] = self.lib.plan_create(pn, N, support, _native.PLAN_GENERIC if generic else 0)
         return p
 
     def plan_for(self, pn: int, N: int, support, shifts_d: torch.Tensor) -> _native.Plan:
@@ -133,9 +140,10 @@ class AbbeEngine:
         return plan
 
     def workspace(self, nbytes: int, slot: str = "t") -> torch.Tensor:
-        ws = self._workspaces.get(slot)
-        if ws is None or ws.numel() < nbytes:
-            ws = self._workspaces[slot] = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=self.device)
+        with self._cache_lock:
+            ws = self._workspaces.get(slot)
+            if ws is None or ws.numel() < nbytes:
+                ws = self._workspaces[slot] = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=self.device)
         return ws
 
     # -- hot path --------------------------------------------------------------------------
