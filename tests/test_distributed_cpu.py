@@ -80,7 +80,7 @@ def test_shard_shifts_partition():
 
 def _peer_worker(rank, world, port, case, out_dir):
     """The peer-memory protocol of distributed.PeerPlanes (publish / gather_sum / wait_consumed) between two
-    PROCESSES, on the CPU emulation (POSIX shared memory stands in for CUDA IPC): 5 images with a rotating root,
+    PROCESSES, on the CPU emulation (POSIX shared memory stands in for CUDA IPC): 7 images over 3 plane slots with a rotating root,
     every image must equal the reference golden."""
     import ctypes as C
     from lithographysimulator_b200.distributed import PeerPlanes
@@ -106,18 +106,19 @@ def _peer_worker(rank, world, port, case, out_dir):
             dist.all_gather_object(out, obj)
             return out
 
-        peers = PeerPlanes(lib, elems, rank, world, exchange)
-        planes = [np.ctypeslib.as_array((C.c_float * elems).from_address(peers.plane_ptr(k))) for k in range(2)]
+        SLOTS = 3                                  # what distributed.ShardedPipeline uses
+        peers = PeerPlanes(lib, elems, rank, world, exchange, slots=SLOTS)
+        planes = [np.ctypeslib.as_array((C.c_float * elems).from_address(peers.plane_ptr(k))) for k in range(SLOTS)]
         wsb = plan.workspace_bytes(0)
         ws = np.zeros(max(wsb, 8), np.uint8)
         fwb = plan.finalize_workspace_bytes()
         fws = np.zeros(max(fwb, 8), np.uint8)
         side = plan.output_side(eps)
         summed = np.zeros(elems, np.float32)
-        for i in range(5):
-            k, seq, root = i % 2, i + 1, i % world
-            if i >= 2:
-                peers.wait_consumed(k, seq - 2)
+        for i in range(7):
+            k, seq, root = i % SLOTS, i + 1, i % world
+            if i >= SLOTS:
+                peers.wait_consumed(k, seq - SLOTS)
             planes[k][:] = 0
             plan.accumulate(mft.ctypes.data, pup.ctypes.data, mine.ctypes.data, None, len(mine), 0,
                             peers.plane_ptr(k), ws.ctypes.data, wsb)
@@ -139,7 +140,7 @@ def test_two_rank_peer_memory_sum_rotating_root(tmp_path):
     H.emu_lib()
     mp.spawn(_peer_worker, args=(2, _free_port(), "demo64_quasar", str(tmp_path)), nprocs=2, join=True)
     ref = H.load_kat()["demo64_quasar"]["image"]
-    for i in range(5):
+    for i in range(7):
         img = np.load(str(tmp_path / f"img{i}.npy"))
         assert O.rel_l2(img, ref) < H.TOL
 
