@@ -214,12 +214,6 @@ template int launch_fast_rows_m<LITHO_INST_M, 32>(const FastRowsParams&, int, li
 template int launch_fast_cols_m<LITHO_INST_M, 32>(const FastColsParams&, litho_stream_t);
 template int fast_ntab_m<LITHO_INST_M, 32>();
 template int fast_tma_cols_m<LITHO_INST_M, 32>(int);
-#if defined(LITHO_WITH_PPT16)  // 16 points per thread: measured 2x slower on B200 (profiles/README.md), not built by default
-template int launch_fast_rows_m<LITHO_INST_M, 16>(const FastRowsParams&, int, litho_stream_t);
-template int launch_fast_cols_m<LITHO_INST_M, 16>(const FastColsParams&, litho_stream_t);
-template int fast_ntab_m<LITHO_INST_M, 16>();
-template int fast_tma_cols_m<LITHO_INST_M, 16>(int);
-#endif
 #endif
 
 template int launch_rows_m<LITHO_INST_M>(int, const RowsParams&, int, int, litho_stream_t);

@@ -512,11 +512,7 @@ static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 static int dispatch_fast_rows(int M, int ppt, const FastRowsParams& P, int gx, litho_stream_t st) {
     switch (M) {
-#if defined(LITHO_WITH_PPT16)
-#define X(m) case m: return ppt == 16 ? launch_fast_rows_m<m, 16>(P, gx, st) : launch_fast_rows_m<m, 32>(P, gx, st);
-#else
 #define X(m) case m: return launch_fast_rows_m<m, 32>(P, gx, st);
-#endif
         LITHO_FOR_EACH_FAST_M(X)
 #undef X
     }
@@ -524,11 +520,7 @@ static int dispatch_fast_rows(int M, int ppt, const FastRowsParams& P, int gx, l
 }
 static int dispatch_fast_cols(int M, int ppt, const FastColsParams& P, litho_stream_t st) {
     switch (M) {
-#if defined(LITHO_WITH_PPT16)
-#define X(m) case m: return ppt == 16 ? launch_fast_cols_m<m, 16>(P, st) : launch_fast_cols_m<m, 32>(P, st);
-#else
 #define X(m) case m: return launch_fast_cols_m<m, 32>(P, st);
-#endif
         LITHO_FOR_EACH_FAST_M(X)
 #undef X
     }
@@ -536,11 +528,7 @@ static int dispatch_fast_cols(int M, int ppt, const FastColsParams& P, litho_str
 }
 static int dispatch_fast_tma_cols(int M, int ppt, int which) {
     switch (M) {
-#if defined(LITHO_WITH_PPT16)
-#define X(m) case m: return ppt == 16 ? fast_tma_cols_m<m, 16>(which) : fast_tma_cols_m<m, 32>(which);
-#else
 #define X(m) case m: return fast_tma_cols_m<m, 32>(which);
-#endif
         LITHO_FOR_EACH_FAST_M(X)
 #undef X
     }
@@ -548,11 +536,7 @@ static int dispatch_fast_tma_cols(int M, int ppt, int which) {
 }
 static int dispatch_fast_ntab(int M, int ppt) {
     switch (M) {
-#if defined(LITHO_WITH_PPT16)
-#define X(m) case m: return ppt == 16 ? fast_ntab_m<m, 16>() : fast_ntab_m<m, 32>();
-#else
 #define X(m) case m: return fast_ntab_m<m, 32>();
-#endif
         LITHO_FOR_EACH_FAST_M(X)
 #undef X
     }
@@ -844,11 +828,6 @@ int litho_plan_create_lines(int pn, int N, const int* bbox, int lines, int flags
         // points per thread of the fast FFTs: 32 (one exchange, 128 regs) or 16 (two exchanges, 64 regs,
         // twice the resident warps); LITHO_FAST_PPT overrides the per-size default for experiments
         p->ppt = 32;
-#if defined(LITHO_WITH_PPT16)
-        if (const char* env = getenv("LITHO_FAST_PPT")) {
-            if (atoi(env) == 16) p->ppt = 16;
-        }
-#endif
         std::vector<cplx> tab = build_fast_tables(Mf, p->ppt);
         if ((int)tab.size() != dispatch_fast_ntab(Mf, p->ppt)) {  // (checked before the padding entry is added)
             delete p;
