@@ -519,15 +519,18 @@ def run_ours(args):
     # kernels next to the persistent compute kernels
     upload_pg, upload_peers = None, None
     if world > 1 and args.upload == "peer":
-        from lithographysimulator_b200.distributed import PeerStaging
+        from lithographysimulator_b200.distributed import PeerStaging, PeerUnavailable
 
         def exchange(obj):
             out = [None] * world
             dist.all_gather_object(out, obj)
             return out
-        upload_peers = PeerStaging(eng.lib, AbbeEngine.peer_staging_bytes(pn, ls_p.dtype), rank, world, exchange)
+        try:
+            upload_peers = PeerStaging(eng.lib, AbbeEngine.peer_staging_bytes(pn, ls_p.dtype), rank, world, exchange)
+        except PeerUnavailable:          # raised on every rank: all fall back to the NCCL all-gather together
+            args.upload = "nccl"
         torch.cuda.synchronize(dev)
-    elif world > 1 and args.upload == "nccl":
+    if world > 1 and args.upload == "nccl":
         upload_pg = dist.new_group(backend="nccl")
 
     def prepare(i):

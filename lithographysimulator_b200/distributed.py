@@ -12,8 +12,49 @@ import torch.distributed as dist
 
 from .imaging import AbbeEngine, _as_c64, _require_cuda, epsilon_n, source_shifts, tensor_from_ptr
 
-__all__ = ["shard_shifts", "abbe_image_sharded", "focus_sweep_sharded", "PeerPlanes", "PeerStaging", "ShardedPipeline",
-           "tensor_from_ptr"]
+__all__ = ["shard_shifts", "abbe_image_sharded", "focus_sweep_sharded", "PeerPlanes", "PeerStaging", "PeerUnavailable",
+           "ShardedPipeline", "tensor_from_ptr"]
+
+
+class PeerUnavailable(RuntimeError):
+    """Peer-mapped buffers could not be set up on every rank (raised on ALL ranks, so callers can fall back together)."""
+
+
+def _map_peers(lib, nbytes: int, rank: int, world: int, exchange):
+    """Allocate a peer-mappable buffer of nbytes on every rank and map everybody else's.  Collective (three calls of
+    `exchange`); a failure on any rank raises PeerUnavailable on every rank after cleaning up."""
+    base, handle, err = 0, None, None
+    try:
+        base, handle = lib.peer_alloc(nbytes)
+    except Exception as e:          # noqa: BLE001 -- reported to the other ranks below
+        err = f"rank {rank}: {e}"
+    handles = exchange(handle)
+    bases = [0] * world
+    if err is None and all(h is not None for h in handles):
+        try:
+            for r in range(world):
+                bases[r] = base if r == rank else lib.peer_open(handles[r])
+        except Exception as e:      # noqa: BLE001
+            err = f"rank {rank}: {e}"
+    elif err is None:
+        err = "a peer could not allocate"
+    errs = exchange(err)
+    if any(e is not None for e in errs):
+        for r, b in enumerate(bases):
+            if r != rank and b:
+                try:
+                    lib.check_peer(lib.litho_peer_close(b), "litho_peer_close")
+                except Exception:   # noqa: BLE001
+                    pass
+        exchange(b"unmapped")       # nobody frees while somebody may still be unmapping
+        if base:
+            try:
+                lib.check_peer(lib.litho_peer_free(base), "litho_peer_free")
+            except Exception:       # noqa: BLE001
+                pass
+        raise PeerUnavailable("; ".join(e for e in errs if e is not None))
+    exchange(b"mapped")             # nobody proceeds (or frees) before every rank has mapped every buffer
+    return base, bases
 
 
 class PeerPlanes:
@@ -39,10 +80,7 @@ class PeerPlanes:
         self.max_peers = MAX_PEERS
         self.plane_bytes = (self.elems * 4 + 255) // 256 * 256
         self.total_bytes = slots * self.plane_bytes + self.MAILBOX_BYTES
-        self.base, handle = lib.peer_alloc(self.total_bytes)
-        handles = exchange(handle)
-        self.bases = [self.base if r == rank else lib.peer_open(handles[r]) for r in range(world)]
-        exchange(b"mapped")      # nobody proceeds (or frees) before every rank has mapped every buffer
+        self.base, self.bases = _map_peers(lib, self.total_bytes, rank, world, exchange)
 
     def plane_ptr(self, slot: int, r: int | None = None) -> int:
         return self.bases[self.rank if r is None else r] + slot * self.plane_bytes
@@ -105,10 +143,7 @@ class PeerStaging:
         self.chunk = (-(-self.nbytes // world) + 255) // 256 * 256          # slice size, 256-byte aligned
         self.slot_bytes = self.chunk * world
         self.total_bytes = slots * self.slot_bytes + self.MAILBOX_BYTES
-        self.base, handle = lib.peer_alloc(self.total_bytes)
-        handles = exchange(handle)
-        self.bases = [self.base if r == rank else lib.peer_open(handles[r]) for r in range(world)]
-        exchange(b"mapped")
+        self.base, self.bases = _map_peers(lib, self.total_bytes, rank, world, exchange)
         self.uses = [0] * slots
 
     def buffer_ptr(self, slot: int, r: int | None = None) -> int:
@@ -192,7 +227,14 @@ class ShardedPipeline:
                 out = [None] * self.world
                 dist.all_gather_object(out, obj, group=group)
                 return out
-            self.peers = PeerPlanes(eng.lib, elems, self.rank, self.world, exchange, slots=self.slots)
+            try:
+                self.peers = PeerPlanes(eng.lib, elems, self.rank, self.world, exchange, slots=self.slots)
+            except PeerUnavailable as e:      # raised on every rank: all fall back to the collective together
+                if self.rank == 0:
+                    import sys
+                    print(f"ShardedPipeline: peer-mapped planes unavailable ({e}); using ncclReduce", file=sys.stderr, flush=True)
+                self.reduce = "nccl"
+        if self.reduce == "peer":
             torch.cuda.synchronize(dev)
             self.planes = [tensor_from_ptr(self.peers.plane_ptr(k), elems, dev) for k in range(self.slots)]
             self.err = tensor_from_ptr(self.peers.err_ptr, 2, dev, torch.int32)

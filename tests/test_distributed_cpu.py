@@ -188,3 +188,46 @@ def test_peer_staging_gathers_all_slices(tmp_path):
     mp.spawn(_staging_worker, args=(3, _free_port(), str(tmp_path)), nprocs=3, join=True)
     for r in range(3):
         assert open(str(tmp_path / f"ok{r}")).read() == "True"
+
+
+def _unavailable_worker(rank, world, port, out_dir):
+    """A rank that cannot allocate (or map) its peer buffer: EVERY rank must get PeerUnavailable, after the same number
+    of collective calls, so that callers can fall back to the NCCL path together."""
+    from lithographysimulator_b200.distributed import PeerPlanes, PeerUnavailable
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lib = H.emu_lib()
+
+        def exchange(obj):
+            out = [None] * world
+            dist.all_gather_object(out, obj)
+            return out
+
+        class Broken:                       # rank 1's allocation fails, rank 0's mapping of it therefore never happens
+            def __getattr__(self, name):
+                return getattr(lib, name)
+
+            def peer_alloc(self, nbytes):
+                raise RuntimeError("no IPC here")
+
+        got = "none"
+        try:
+            PeerPlanes(Broken() if rank == 1 else lib, 1000, rank, world, exchange)
+        except PeerUnavailable as e:
+            got = "unavailable:" + str(e)
+        dist.barrier()                      # still in step with each other
+        ok = PeerPlanes(lib, 1000, rank, world, exchange)      # and a healthy set-up works right after
+        ok.close()
+        open(os.path.join(out_dir, f"r{rank}"), "w").write(got)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_unavailable_is_raised_on_every_rank(tmp_path):
+    H.emu_lib()
+    mp.spawn(_unavailable_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        got = open(str(tmp_path / f"r{r}")).read()
+        assert got.startswith("unavailable:") and "no IPC here" in got, got
